@@ -1,0 +1,2 @@
+#include "ode_instantiate.cuh"
+ODE_B200_DEFINE_SYSTEM(SysKepler, kepler)

@@ -1,0 +1,716 @@
+/*
+ * ode_b200.cu -- implementation of the C ABI (include/ode_b200.h): system registry,
+ * constructors, per-GPU contexts, the launchers of the persistent step-loop kernels,
+ * the multi-GPU sharding driver and small device utilities (FP64 peak probe, batched
+ * ContinuousOutputModel::evaluate, pow/exp clone probes).
+ *
+ * No CPU fallback exists anywhere in this file: without a usable CUDA device every
+ * integrate entry point returns an error.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "ode_b200.h"
+#include "ode_device.cuh"
+#include "ode_jit.h"
+#include "ode_registry.h"
+
+using namespace ode_b200;
+
+/* ------------------------------------------------------------------ errors */
+static thread_local std::string g_last_error = "";
+
+static int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return fail(ODE_B200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));    \
+    } while (0)
+
+extern "C" const char* ode_b200_last_error(void) { return g_last_error.c_str(); }
+extern "C" int ode_b200_abi_version(void) { return ODE_B200_ABI_VERSION; }
+extern "C" int ode_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+/* ------------------------------------------------------------------ registry */
+extern "C" {
+extern const SystemEntry ode_b200_entry_lorenz, ode_b200_entry_kepler, ode_b200_entry_cr3bp,
+    ode_b200_entry_robertson, ode_b200_entry_bouncing_ball, ode_b200_entry_threebody18,
+    ode_b200_entry_test_rk4_1, ode_b200_entry_test_rk4_2, ode_b200_entry_test_exp,
+    ode_b200_entry_test_exp_stop, ode_b200_entry_test_cubic, ode_b200_entry_test_cubic_stop;
+}
+static const SystemEntry* const kBuiltins[] = {
+    &ode_b200_entry_lorenz,        &ode_b200_entry_kepler,      &ode_b200_entry_cr3bp,
+    &ode_b200_entry_robertson,     &ode_b200_entry_bouncing_ball, &ode_b200_entry_threebody18,
+    &ode_b200_entry_test_rk4_1,    &ode_b200_entry_test_rk4_2,  &ode_b200_entry_test_exp,
+    &ode_b200_entry_test_exp_stop, &ode_b200_entry_test_cubic,  &ode_b200_entry_test_cubic_stop,
+};
+static constexpr int kNumBuiltins = sizeof(kBuiltins) / sizeof(kBuiltins[0]);
+
+extern "C" int ode_b200_system_builtin(const char* name) {
+    if (!name) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "name is NULL");
+    for (int i = 0; i < kNumBuiltins; ++i)
+        if (!strcmp(kBuiltins[i]->name, name)) return i;
+    return fail(ODE_B200_ERR_UNKNOWN_SYSTEM, std::string("unknown built-in system: ") + name);
+}
+
+struct SysInfo {
+    const char* name;
+    int dim, n_params;
+    bool jit;
+};
+static bool sys_info(int id, SysInfo* s) {
+    if (id >= 0 && id < kNumBuiltins) {
+        *s = {kBuiltins[id]->name, kBuiltins[id]->dim, kBuiltins[id]->n_params, false};
+        return true;
+    }
+    const JitSystem* j = jit_system(id - kNumBuiltins);
+    if (!j) return false;
+    *s = {j->name.c_str(), j->dim, j->n_params, true};
+    return true;
+}
+extern "C" int ode_b200_system_dim(int id) {
+    SysInfo s;
+    return sys_info(id, &s) ? s.dim : fail(ODE_B200_ERR_UNKNOWN_SYSTEM, "bad sys_id");
+}
+extern "C" int ode_b200_system_n_params(int id) {
+    SysInfo s;
+    return sys_info(id, &s) ? s.n_params : fail(ODE_B200_ERR_UNKNOWN_SYSTEM, "bad sys_id");
+}
+extern "C" const char* ode_b200_system_name(int id) {
+    SysInfo s;
+    return sys_info(id, &s) ? s.name : nullptr;
+}
+extern "C" int ode_b200_system_from_source(const char* name, int dim, int n_params, const char* rhs_body,
+                                           const char* solout_body) {
+    if (!name || !rhs_body || dim < 1 || dim > ODE_B200_MAX_DIM || n_params < 0 || n_params > ODE_B200_MAX_PARAMS)
+        return fail(ODE_B200_ERR_INVALID_ARGUMENT, "system_from_source: bad arguments");
+    std::string err;
+    int id = jit_register(name, dim, n_params, rhs_body, solout_body, &err);
+    if (id < 0) return fail(ODE_B200_ERR_COMPILE, err);
+    return kNumBuiltins + id;
+}
+
+/* ------------------------------------------------------------------ constructors */
+static const double kEps = 2.220446049250313e-16; /* f64::EPSILON */
+
+/* Dopri5::new (dopri5.rs:76-105, controller defaults :14-27); Dop853::new (dop853.rs:76-109, :14-27) */
+extern "C" int ode_b200_config_new(int method, double x, double x_end, double dx, double rtol, double atol,
+                                   ode_b200_config* c) {
+    if (!c) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "config is NULL");
+    memset(c, 0, sizeof(*c));
+    c->method = method;
+    c->out_type = ODE_B200_OUT_DENSE;
+    c->x0 = x;
+    c->x_end = x_end;
+    c->dx = dx;
+    c->rtol = rtol;
+    c->atol = atol;
+    c->safety_factor = 0.9;
+    c->h_max = x_end - x;
+    c->h0 = 0.0;
+    c->uround = kEps;
+    c->n_max = 100000;
+    c->n_stiff = 1000;
+    if (method == ODE_B200_DOPRI5) {
+        volatile double b = 0.04; /* keep the two roundings of `0.2 - 0.04 * 0.75` */
+        c->beta = 0.04;
+        c->alpha = 0.2 - b * 0.75;
+        c->fac_max = 10.0;
+        c->fac_min = 0.2;
+    } else if (method == ODE_B200_DOP853) {
+        c->beta = 0.0;
+        c->alpha = 1.0 / 8.0;
+        c->fac_max = 6.0;
+        c->fac_min = 0.333;
+    } else {
+        return fail(ODE_B200_ERR_INVALID_ARGUMENT, "config_new: method must be DOPRI5 or DOP853");
+    }
+    return ODE_B200_SUCCESS;
+}
+
+/* Dopri5::from_param (dopri5.rs:129-184); Dop853::from_param (dop853.rs:133-192) */
+extern "C" int ode_b200_config_from_param(int method, double x, double x_end, double dx, double rtol, double atol,
+                                          double safety_factor, double beta, double fac_min, double fac_max,
+                                          double h_max, double h, uint32_t n_max, uint32_t n_stiff, int out_type,
+                                          ode_b200_config* c) {
+    if (!c) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "config is NULL");
+    if (out_type < ODE_B200_OUT_DENSE || out_type > ODE_B200_OUT_CONTINUOUS)
+        return fail(ODE_B200_ERR_INVALID_ARGUMENT, "config_from_param: bad out_type");
+    memset(c, 0, sizeof(*c));
+    c->method = method;
+    c->out_type = out_type;
+    c->x0 = x;
+    c->x_end = x_end;
+    c->dx = dx;
+    c->rtol = rtol;
+    c->atol = atol;
+    c->safety_factor = safety_factor;
+    c->beta = beta;
+    c->fac_min = fac_min;
+    c->fac_max = fac_max;
+    c->h_max = h_max;
+    c->h0 = h;
+    c->uround = kEps;
+    c->n_max = n_max;
+    c->n_stiff = n_stiff;
+    volatile double b = beta;
+    if (method == ODE_B200_DOPRI5) {
+        volatile double t = b * 0.75;
+        c->alpha = 0.2 - t;
+    } else if (method == ODE_B200_DOP853) {
+        volatile double t = b * 0.2;
+        c->alpha = 1.0 / 8.0 - t;
+    } else {
+        return fail(ODE_B200_ERR_INVALID_ARGUMENT, "config_from_param: method must be DOPRI5 or DOP853");
+    }
+    return ODE_B200_SUCCESS;
+}
+
+/* Rk4::new (rk4.rs:42-68) */
+extern "C" int ode_b200_config_rk4(double x, double x_end, double step_size, ode_b200_config* c) {
+    if (!c) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "config is NULL");
+    memset(c, 0, sizeof(*c));
+    c->method = ODE_B200_RK4;
+    c->out_type = ODE_B200_OUT_SPARSE;
+    c->x0 = x;
+    c->x_end = x_end;
+    c->step_size = step_size;
+    return ODE_B200_SUCCESS;
+}
+
+/* ------------------------------------------------------------------ contexts */
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct ode_b200_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    int use_queue = 1;
+    unsigned long long* queue = nullptr;
+    uint64_t launches = 0;
+    double last_ms = 0.0;
+    /* grow-only workspace for the host-buffer entry points */
+    DevBuf y0, params, y_final, x_final, h_next, num_eval, accepted, rejected, n_step, status, out_x, out_y,
+        out_count, com_lower, com_break, com_step, com_coef, com_count, scratch0, scratch1, scratch2;
+};
+
+static int ensure(ode_b200_ctx* c, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return 0;
+    if (b.p) CUDA_TRY(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    CUDA_TRY(cudaMalloc(&b.p, bytes));
+    b.cap = bytes;
+    (void)c;
+    return 0;
+}
+
+extern "C" ode_b200_ctx* ode_b200_create(int device) {
+    int n = ode_b200_device_count();
+    if (n <= 0) {
+        fail(ODE_B200_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
+        return nullptr;
+    }
+    if (device < 0 || device >= n) {
+        fail(ODE_B200_ERR_INVALID_ARGUMENT, "device index out of range");
+        return nullptr;
+    }
+    ode_b200_ctx* c = new ode_b200_ctx();
+    c->device = device;
+    bool ok = cudaSetDevice(device) == cudaSuccess &&
+              cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess &&
+              cudaMalloc((void**)&c->queue, 256) == cudaSuccess;
+    if (!ok) {
+        fail(ODE_B200_ERR_CUDA, std::string("context creation failed: ") + cudaGetErrorString(cudaGetLastError()));
+        delete c;
+        return nullptr;
+    }
+    return c;
+}
+
+extern "C" void ode_b200_destroy(ode_b200_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf* bufs[] = {&c->y0, &c->params, &c->y_final, &c->x_final, &c->h_next, &c->num_eval, &c->accepted,
+                      &c->rejected, &c->n_step, &c->status, &c->out_x, &c->out_y, &c->out_count, &c->com_lower,
+                      &c->com_break, &c->com_step, &c->com_coef, &c->com_count, &c->scratch0, &c->scratch1,
+                      &c->scratch2};
+    for (DevBuf* b : bufs)
+        if (b->p) cudaFree(b->p);
+    if (c->queue) cudaFree(c->queue);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" double ode_b200_last_kernel_ms(const ode_b200_ctx* c) {
+    if (!c || !c->timed) return 0.0;
+    float ms = 0.f;
+    if (cudaEventSynchronize(c->ev1) != cudaSuccess) return 0.0;
+    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) return 0.0;
+    return (double)ms;
+}
+extern "C" uint64_t ode_b200_launch_count(const ode_b200_ctx* c) { return c ? c->launches : 0; }
+extern "C" int ode_b200_set_work_queue(ode_b200_ctx* c, int enabled) {
+    if (!c) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    c->use_queue = enabled ? 1 : 0;
+    return ODE_B200_SUCCESS;
+}
+
+/* ------------------------------------------------------------------ launch */
+static int validate(const ode_b200_config* cfg, const SysInfo& s, int64_t n, const double* y0,
+                    const double* params, const ode_b200_outputs* out) {
+    if (!cfg || !out) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "cfg / out is NULL");
+    if (n < 0) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "n_traj < 0");
+    if (n > 0 && !y0) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "y0 is NULL");
+    if (n > 0 && s.n_params > 0 && !params) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "params is NULL");
+    if (cfg->method < ODE_B200_RK4 || cfg->method > ODE_B200_DOP853)
+        return fail(ODE_B200_ERR_INVALID_ARGUMENT, "bad method");
+    if (cfg->out_type < ODE_B200_OUT_DENSE || cfg->out_type > ODE_B200_OUT_CONTINUOUS)
+        return fail(ODE_B200_ERR_INVALID_ARGUMENT, "bad out_type");
+    if (out->out_cap < 0 || out->com_cap < 0) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "negative capacity");
+    if (out->out_cap > 0 && (!out->out_x || !out->out_y))
+        return fail(ODE_B200_ERR_INVALID_ARGUMENT, "out_cap > 0 needs out_x and out_y");
+    if (out->com_cap > 0 && (!out->com_break || !out->com_step || !out->com_coef))
+        return fail(ODE_B200_ERR_INVALID_ARGUMENT, "com_cap > 0 needs com_break, com_step and com_coef");
+    return 0;
+}
+
+__global__ void fill_unsupported_kernel(KernelArgs a, int dim) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n_traj) return;
+    const ode_b200_outputs& o = a.out;
+    if (o.y_final)
+        for (int c = 0; c < dim; ++c) o.y_final[(size_t)c * a.n_traj + t] = a.y0[(size_t)c * a.n_traj + t];
+    if (o.x_final) o.x_final[t] = a.cfg.x0;
+    if (o.h_next) o.h_next[t] = 0.0;
+    if (o.num_eval) o.num_eval[t] = 0;
+    if (o.accepted) o.accepted[t] = 0;
+    if (o.rejected) o.rejected[t] = 0;
+    if (o.n_step) o.n_step[t] = 0;
+    if (o.status) o.status[t] = ODE_B200_UNSUPPORTED_DOMAIN;
+    if (o.out_count) o.out_count[t] = 0;
+    if (o.com_count) o.com_count[t] = 0;
+    if (o.com_lower) o.com_lower[t] = 0.0;
+}
+
+/* enqueue the step-loop kernel for device-resident inputs/outputs on `stream` */
+static int launch_device(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg, int64_t n, const double* y0,
+                         const double* params, int per_traj, const ode_b200_outputs* out, cudaStream_t stream) {
+    SysInfo s;
+    if (!sys_info(sys_id, &s)) return fail(ODE_B200_ERR_UNKNOWN_SYSTEM, "bad sys_id");
+    if (int rc = validate(cfg, s, n, y0, params, out)) return rc;
+    if (n == 0) return ODE_B200_SUCCESS;
+    CUDA_TRY(cudaSetDevice(c->device));
+
+    KernelArgs ka;
+    memset(&ka, 0, sizeof(ka));
+    ka.cfg = *cfg;
+    /* Controller::new, controller.rs:29-49 */
+    ka.facc1 = 1.0 / cfg->fac_min;
+    ka.facc2 = 1.0 / cfg->fac_max;
+    ka.h_max_abs = fabs(cfg->h_max);
+    ka.posneg = (cfg->x_end - cfg->x0) > 0.0 ? 1.0 : -1.0; /* sign(1, x_end - x) */
+    ka.n_traj = n;
+    ka.y0 = y0;
+    ka.params = params;
+    ka.params_per_traj = per_traj ? 1 : 0;
+    ka.use_queue = c->use_queue;
+    ka.queue = c->queue;
+    ka.out = *out;
+    if (ka.out.out_cap == 0) ka.out.out_x = ka.out.out_y = nullptr;
+    if (ka.out.com_cap == 0) ka.out.com_break = ka.out.com_step = ka.out.com_coef = nullptr;
+
+    const int block = kBlockThreads;
+    const long long blocks_all = (n + block - 1) / block;
+
+    /* `accepted % n_stiff` panics in the reference when n_stiff == 0 */
+    if (cfg->method != ODE_B200_RK4 && cfg->n_stiff == 0) {
+        fill_unsupported_kernel<<<(unsigned)blocks_all, block, 0, stream>>>(ka, s.dim);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return ODE_B200_SUCCESS;
+    }
+
+    CUDA_TRY(cudaMemsetAsync(c->queue, 0, sizeof(unsigned long long), stream));
+    if (stream == c->stream) CUDA_TRY(cudaEventRecord(c->ev0, stream));
+    if (!s.jit) {
+        const void* fn = kBuiltins[sys_id]->kernels[cfg->method][cfg->out_type];
+        int per_sm = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block, 0));
+        if (per_sm < 1) return fail(ODE_B200_ERR_CUDA, "kernel does not fit on an SM");
+        long long grid = blocks_all;
+        if (c->use_queue) grid = std::min<long long>(blocks_all, (long long)c->num_sms * per_sm);
+        void* args[] = {&ka};
+        CUDA_TRY(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(block), args, 0, stream));
+    } else {
+        std::string err;
+        if (!jit_launch(sys_id - kNumBuiltins, c->device, c->num_sms, cfg->method, cfg->out_type, &ka, sizeof(ka),
+                        block, blocks_all, c->use_queue, (void*)stream, &err))
+            return fail(ODE_B200_ERR_COMPILE, err);
+    }
+    if (stream == c->stream) {
+        CUDA_TRY(cudaEventRecord(c->ev1, stream));
+        c->timed = true;
+    }
+    c->launches++;
+    return ODE_B200_SUCCESS;
+}
+
+extern "C" int ode_b200_integrate_batch_device(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg,
+                                               int64_t n, const double* y0, const double* params, int per_traj,
+                                               const ode_b200_outputs* out, void* cuda_stream) {
+    if (!c) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+    return launch_device(c, sys_id, cfg, n, y0, params, per_traj, out, st);
+}
+
+/*
+ * Host-buffer path for the trajectory range [lo, hi) of a batch of n_total: stage the
+ * range's column block of the SoA inputs, run, copy the range's outputs back into the
+ * caller's full-size arrays. [0, n_total) on one context is ode_b200_integrate_batch;
+ * one range per GPU is the multi-GPU shard.
+ */
+static int integrate_range(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg, int64_t n_total, int64_t lo,
+                           int64_t hi, const double* y0, const double* params, int per_traj,
+                           const ode_b200_outputs* out) {
+    SysInfo s;
+    if (!sys_info(sys_id, &s)) return fail(ODE_B200_ERR_UNKNOWN_SYSTEM, "bad sys_id");
+    if (int rc = validate(cfg, s, n_total, y0, params, out)) return rc;
+    const int64_t n = hi - lo;
+    if (n <= 0) return ODE_B200_SUCCESS;
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t d = (size_t)s.dim, np = (size_t)s.n_params;
+    const int m = cfg->method == ODE_B200_DOPRI5 ? 5 : 8;
+    cudaStream_t st = c->stream;
+
+    if (ensure(c, c->y0, d * n * 8)) return ODE_B200_ERR_CUDA;
+    CUDA_TRY(cudaMemcpy2DAsync(c->y0.p, n * 8, y0 + lo, n_total * 8, n * 8, d, cudaMemcpyHostToDevice, st));
+    if (np) {
+        if (per_traj) {
+            if (ensure(c, c->params, np * n * 8)) return ODE_B200_ERR_CUDA;
+            CUDA_TRY(cudaMemcpy2DAsync(c->params.p, n * 8, params + lo, n_total * 8, n * 8, np,
+                                       cudaMemcpyHostToDevice, st));
+        } else {
+            if (ensure(c, c->params, np * 8)) return ODE_B200_ERR_CUDA;
+            CUDA_TRY(cudaMemcpyAsync(c->params.p, params, np * 8, cudaMemcpyHostToDevice, st));
+        }
+    }
+    ode_b200_outputs dv;
+    memset(&dv, 0, sizeof(dv));
+#define WANT(field, buf, bytes)                                   \
+    if (out->field) {                                             \
+        if (ensure(c, c->buf, (bytes))) return ODE_B200_ERR_CUDA; \
+        dv.field = (decltype(dv.field))c->buf.p;                  \
+    }
+    WANT(y_final, y_final, d * n * 8)
+    WANT(x_final, x_final, n * 8)
+    WANT(h_next, h_next, n * 8)
+    WANT(num_eval, num_eval, n * 4)
+    WANT(accepted, accepted, n * 4)
+    WANT(rejected, rejected, n * 4)
+    WANT(n_step, n_step, n * 4)
+    WANT(status, status, n * 4)
+    WANT(out_count, out_count, n * 4)
+    WANT(com_count, com_count, n * 4)
+    WANT(com_lower, com_lower, n * 8)
+    if (out->out_cap > 0) {
+        dv.out_cap = out->out_cap;
+        WANT(out_x, out_x, (size_t)n * out->out_cap * 8)
+        WANT(out_y, out_y, (size_t)n * out->out_cap * d * 8)
+    }
+    if (out->com_cap > 0) {
+        dv.com_cap = out->com_cap;
+        WANT(com_break, com_break, (size_t)n * out->com_cap * 8)
+        WANT(com_step, com_step, (size_t)n * out->com_cap * 8)
+        WANT(com_coef, com_coef, (size_t)n * out->com_cap * m * d * 8)
+    }
+#undef WANT
+    if (int rc = launch_device(c, sys_id, cfg, n, (const double*)c->y0.p, (const double*)c->params.p, per_traj,
+                               &dv, st))
+        return rc;
+
+    if (out->y_final)
+        CUDA_TRY(cudaMemcpy2DAsync(out->y_final + lo, n_total * 8, dv.y_final, n * 8, n * 8, d,
+                                   cudaMemcpyDeviceToHost, st));
+#define BACK(field, elem_bytes, per)                                                                      \
+    if (out->field)                                                                                       \
+        CUDA_TRY(cudaMemcpyAsync((char*)out->field + (size_t)lo * (per) * (elem_bytes), dv.field,         \
+                                 (size_t)n * (per) * (elem_bytes), cudaMemcpyDeviceToHost, st));
+    BACK(x_final, 8, 1)
+    BACK(h_next, 8, 1)
+    BACK(num_eval, 4, 1)
+    BACK(accepted, 4, 1)
+    BACK(rejected, 4, 1)
+    BACK(n_step, 4, 1)
+    BACK(status, 4, 1)
+    BACK(out_count, 4, 1)
+    BACK(com_count, 4, 1)
+    BACK(com_lower, 8, 1)
+    if (out->out_cap > 0) {
+        BACK(out_x, 8, (size_t)out->out_cap)
+        BACK(out_y, 8, (size_t)out->out_cap * d)
+    }
+    if (out->com_cap > 0) {
+        BACK(com_break, 8, (size_t)out->com_cap)
+        BACK(com_step, 8, (size_t)out->com_cap)
+        BACK(com_coef, 8, (size_t)out->com_cap * m * d)
+    }
+#undef BACK
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return ODE_B200_SUCCESS;
+}
+
+extern "C" int ode_b200_integrate_batch(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg, int64_t n,
+                                        const double* y0, const double* params, int per_traj,
+                                        const ode_b200_outputs* out) {
+    if (!c) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    return integrate_range(c, sys_id, cfg, n, 0, n, y0, params, per_traj, out);
+}
+
+/* contiguous index ranges, one host thread + context + stream per GPU, no collective */
+extern "C" int ode_b200_integrate_batch_multi(int sys_id, const ode_b200_config* cfg, int64_t n,
+                                              const double* y0, const double* params, int per_traj, int n_gpus,
+                                              const ode_b200_outputs* out) {
+    const int avail = ode_b200_device_count();
+    if (avail <= 0) return fail(ODE_B200_ERR_NO_DEVICE, "no CUDA device available (no CPU fallback)");
+    if (n_gpus < 1 || n_gpus > avail) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "n_gpus out of range");
+    static std::mutex mu;
+    static std::vector<ode_b200_ctx*> ctxs;
+    {
+        std::lock_guard<std::mutex> g(mu);
+        while ((int)ctxs.size() < n_gpus) {
+            ode_b200_ctx* c = ode_b200_create((int)ctxs.size());
+            if (!c) return ODE_B200_ERR_CUDA;
+            ctxs.push_back(c);
+        }
+    }
+    const int64_t per = (n + n_gpus - 1) / n_gpus;
+    std::vector<int> rcs(n_gpus, 0);
+    std::vector<std::string> errs(n_gpus);
+    std::vector<std::thread> th;
+    for (int g = 0; g < n_gpus; ++g) {
+        th.emplace_back([&, g]() {
+            const int64_t lo = std::min<int64_t>(n, per * g), hi = std::min<int64_t>(n, per * (g + 1));
+            rcs[g] = integrate_range(ctxs[g], sys_id, cfg, n, lo, hi, y0, params, per_traj, out);
+            if (rcs[g]) errs[g] = g_last_error;
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int g = 0; g < n_gpus; ++g)
+        if (rcs[g]) return fail(rcs[g], "gpu " + std::to_string(g) + ": " + errs[g]);
+    return ODE_B200_SUCCESS;
+}
+
+/* ------------------------------------------------------------------ FP64 peak probe */
+/* 8 independent DFMA chains per thread; counts FP64-pipe thread-instructions per second */
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, int iters, double seed) {
+    double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6,
+           a7 = seed + 7;
+    const double m = 0.9999999, c = 1e-9 * threadIdx.x;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = fma(a0, m, c);
+            a1 = fma(a1, m, c);
+            a2 = fma(a2, m, c);
+            a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c);
+            a5 = fma(a5, m, c);
+            a6 = fma(a6, m, c);
+            a7 = fma(a7, m, c);
+        }
+    }
+    double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 123.456) sink[0] = r;
+}
+
+extern "C" int ode_b200_measure_fp64_peak(int device, double* inst_per_s, double* sm_mhz_est) {
+    if (ode_b200_device_count() <= 0) return fail(ODE_B200_ERR_NO_DEVICE, "no CUDA device");
+    CUDA_TRY(cudaSetDevice(device));
+    int sms = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    double* sink = nullptr;
+    CUDA_TRY(cudaMalloc(&sink, 8));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int iters = 4096, grid = sms * 8, block = 256;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0));
+        fp64_peak_kernel<<<grid, block>>>(sink, iters, 1.0 + rep);
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double inst = (double)grid * block * (double)iters * 16.0 * 8.0;
+        if (rep > 0) best = std::max(best, inst / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    if (inst_per_s) *inst_per_s = best;
+    /* 64 FP64 lanes per SM: implied SM clock if the pipe was saturated */
+    if (sm_mhz_est) *sm_mhz_est = best / (64.0 * sms) * 1e-6;
+    return ODE_B200_SUCCESS;
+}
+
+/* ------------------------------------------------------------------ COM::evaluate */
+/* continuous_output_model.rs:31-56 (evaluate) and :86-104 (get_interval_index); one thread
+ * per (trajectory, query). m and dim are runtime here: this kernel is HBM/latency bound. */
+__global__ void com_evaluate_kernel(long long n, int dim, int m, long long cap, const double* lower,
+                                    const double* brk, const double* stp, const double* coef,
+                                    const unsigned* count, long long nq, const double* xq, double* y,
+                                    unsigned char* found) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n * nq) return;
+    const long long t = g / nq, qi = g % nq;
+    const double x = xq[qi];
+    const unsigned cnt = (unsigned)min((long long)count[t], cap);
+    const double* bp = brk + (size_t)t * cap;
+    unsigned char ok = 0;
+    if (!(x < lower[t]) && m > 0) {
+        unsigned lo = 0, hi = cnt;
+        long long hit = -1;
+        while (lo < hi) {
+            const unsigned mid = lo + (hi - lo) / 2;
+            const double b = bp[mid];
+            if (b == x) {
+                hit = mid;
+                break;
+            }
+            if (b < x)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        long long index = hit >= 0 ? hit : (lo < cnt ? (long long)lo : -1);
+        if (index >= 0) {
+            const double lb = index == 0 ? lower[t] : bp[index - 1];
+            const double theta = (x - lb) / stp[(size_t)t * cap + index], theta1 = 1.0 - theta;
+            const double* c = coef + ((size_t)t * cap + index) * m * dim;
+            for (int i = 0; i < dim; ++i) {
+                double r = c[(size_t)(m - 1) * dim + i];
+                for (int q = m - 2; q >= 0; --q) r = c[(size_t)q * dim + i] + r * ((q % 2 == 0) ? theta : theta1);
+                y[(size_t)g * dim + i] = r;
+            }
+            ok = 1;
+        }
+    }
+    found[g] = ok;
+}
+
+extern "C" int ode_b200_com_evaluate(ode_b200_ctx* c, int64_t n, int dim, int m, int64_t cap,
+                                     const double* lower, const double* brk, const double* stp,
+                                     const double* coef, const uint32_t* count, int64_t nq, const double* xq,
+                                     double* y, uint8_t* found) {
+    if (!c) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    if (n < 0 || nq < 0 || dim < 1 || m < 0 || cap < 1 || !lower || !brk || !stp || !coef || !count || !xq || !y ||
+        !found)
+        return fail(ODE_B200_ERR_INVALID_ARGUMENT, "com_evaluate: bad arguments");
+    if (n == 0 || nq == 0) return ODE_B200_SUCCESS;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t nb = (size_t)n * cap * 8, nc = (size_t)n * cap * m * dim * 8;
+    if (ensure(c, c->com_lower, n * 8) || ensure(c, c->com_break, nb) || ensure(c, c->com_step, nb) ||
+        ensure(c, c->com_coef, nc) || ensure(c, c->com_count, n * 4) || ensure(c, c->scratch0, nq * 8) ||
+        ensure(c, c->scratch1, (size_t)n * nq * dim * 8) || ensure(c, c->scratch2, (size_t)n * nq))
+        return ODE_B200_ERR_CUDA;
+    CUDA_TRY(cudaMemcpyAsync(c->com_lower.p, lower, n * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(c->com_break.p, brk, nb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(c->com_step.p, stp, nb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(c->com_coef.p, coef, nc, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(c->com_count.p, count, n * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(c->scratch0.p, xq, nq * 8, cudaMemcpyHostToDevice, st));
+    const long long total = (long long)n * nq;
+    com_evaluate_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        n, dim, m, cap, (const double*)c->com_lower.p, (const double*)c->com_break.p,
+        (const double*)c->com_step.p, (const double*)c->com_coef.p, (const unsigned*)c->com_count.p, nq,
+        (const double*)c->scratch0.p, (double*)c->scratch1.p, (unsigned char*)c->scratch2.p);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(y, c->scratch1.p, (size_t)total * dim * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(found, c->scratch2.p, (size_t)total, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return ODE_B200_SUCCESS;
+}
+
+/* ------------------------------------------------------------------ introspection */
+extern "C" double ode_b200_tableau(const char* w, int i, int j) {
+    if (!w) return NAN;
+    auto in = [](int v, int n) { return v >= 0 && v < n; };
+    if (!strcmp(w, "a5")) return in(i, 7) && in(j, 7) ? TabDp5::a(i, j) : NAN;
+    if (!strcmp(w, "c5")) return in(i, 7) ? TabDp5::c(i) : NAN;
+    if (!strcmp(w, "d5")) return in(i, 7) ? TabDp5::d(i) : NAN;
+    if (!strcmp(w, "e5")) return in(i, 7) ? TabDp5::e(i) : NAN;
+    if (!strcmp(w, "a8")) return in(i, 16) && in(j, 16) ? TabDp8::a(i, j) : NAN;
+    if (!strcmp(w, "b8")) return in(i, 12) ? TabDp8::b(i) : NAN;
+    if (!strcmp(w, "bhh8")) return in(i, 3) ? TabDp8::bhh(i) : NAN;
+    if (!strcmp(w, "c8")) return in(i, 16) ? TabDp8::c(i) : NAN;
+    if (!strcmp(w, "d8")) return in(i, 4) && in(j, 16) ? TabDp8::d(i, j) : NAN;
+    if (!strcmp(w, "e8")) return in(i, 16) ? TabDp8::e(i) : NAN;
+    return NAN;
+}
+
+__global__ void debug_pow_kernel(long long n, const double* x, const double* y, double* o) {
+    stage_tables_();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) o[i] = y ? pow_d(x[i], y[i]) : exp_d(x[i]);
+}
+
+static int debug_fn(ode_b200_ctx* c, int64_t n, const double* x, const double* y, double* o) {
+    if (!c) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    if (n <= 0) return ODE_B200_SUCCESS;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (ensure(c, c->scratch0, n * 8) || ensure(c, c->scratch1, n * 8) || ensure(c, c->scratch2, n * 8))
+        return ODE_B200_ERR_CUDA;
+    cudaStream_t st = c->stream;
+    CUDA_TRY(cudaMemcpyAsync(c->scratch0.p, x, n * 8, cudaMemcpyHostToDevice, st));
+    if (y) CUDA_TRY(cudaMemcpyAsync(c->scratch1.p, y, n * 8, cudaMemcpyHostToDevice, st));
+    debug_pow_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, (const double*)c->scratch0.p,
+                                                                  y ? (const double*)c->scratch1.p : nullptr,
+                                                                  (double*)c->scratch2.p);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(o, c->scratch2.p, n * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return ODE_B200_SUCCESS;
+}
+extern "C" int ode_b200_debug_pow(ode_b200_ctx* c, int64_t n, const double* x, const double* y, double* o) {
+    if (!x || !y || !o) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "NULL pointer");
+    return debug_fn(c, n, x, y, o);
+}
+extern "C" int ode_b200_debug_exp(ode_b200_ctx* c, int64_t n, const double* x, double* o) {
+    if (!x || !o) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "NULL pointer");
+    return debug_fn(c, n, x, nullptr, o);
+}

@@ -1,0 +1,24 @@
+/*
+ * ode_instantiate.cuh -- instantiate the step-loop kernels of one system ahead of time.
+ * One translation unit per built-in system (inst_*.cu) so `make -j` compiles them in parallel.
+ * Dop853 ignores OutputType::Continuous (it behaves like Sparse: dop853.rs:398,540-542).
+ */
+#pragma once
+
+#include "ode_kernels.cuh"
+#include "ode_registry.h"
+#include "ode_systems.cuh"
+
+#define ODE_B200_KPTR(...) ((const void*)&ode_b200::ode_step_loop_kernel<__VA_ARGS__>)
+
+#define ODE_B200_DEFINE_SYSTEM(SYS, NAME)                                                               \
+    extern "C" const ode_b200::SystemEntry ode_b200_entry_##NAME = {                                    \
+        #NAME, ode_b200::SYS::DIM, ode_b200::SYS::NP, ode_b200::SYS::HAS_SOLOUT ? 1 : 0,                 \
+        {{ODE_B200_KPTR(ode_b200::Rk4Stepper<ode_b200::SYS>), ODE_B200_KPTR(ode_b200::Rk4Stepper<ode_b200::SYS>), \
+          ODE_B200_KPTR(ode_b200::Rk4Stepper<ode_b200::SYS>)},                                           \
+         {ODE_B200_KPTR(ode_b200::Dopri5Stepper<ode_b200::SYS, ODE_B200_OUT_DENSE>),                     \
+          ODE_B200_KPTR(ode_b200::Dopri5Stepper<ode_b200::SYS, ODE_B200_OUT_SPARSE>),                    \
+          ODE_B200_KPTR(ode_b200::Dopri5Stepper<ode_b200::SYS, ODE_B200_OUT_CONTINUOUS>)},               \
+         {ODE_B200_KPTR(ode_b200::Dop853Stepper<ode_b200::SYS, ODE_B200_OUT_DENSE>),                     \
+          ODE_B200_KPTR(ode_b200::Dop853Stepper<ode_b200::SYS, ODE_B200_OUT_SPARSE>),                    \
+          ODE_B200_KPTR(ode_b200::Dop853Stepper<ode_b200::SYS, ODE_B200_OUT_SPARSE>)}}};

@@ -1,0 +1,253 @@
+/*
+ * ode_jit.cpp -- NVRTC path for user-registered systems (see ode_jit.h).
+ *
+ * The reference lets users implement `trait System` in Rust (src/dop_shared.rs:31-42) and
+ * monomorphises the solver around it. The device equivalent of that monomorphisation is to
+ * compile the kernel template around the user's rhs/solout at run time: the generated
+ * translation unit defines `struct SysUser` from the two function bodies and explicitly
+ * instantiates ode_step_loop_kernel<Stepper<SysUser, OUT>> for the requested method and
+ * output type only.
+ */
+#include "ode_jit.h"
+
+#include <cuda.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <map>
+#include <memory>
+#include <mutex>
+#include <tuple>
+#include <vector>
+
+#include "ode_b200.h"
+#include "ode_embedded_headers.inc"
+
+namespace ode_b200 {
+
+namespace {
+
+struct Api {
+    bool ok = false;
+    std::string why;
+    /* nvrtc */
+    nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*,
+                                 const char* const*) = nullptr;
+    nvrtcResult (*DestroyProgram)(nvrtcProgram*) = nullptr;
+    nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+    nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
+    nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
+    nvrtcResult (*AddNameExpression)(nvrtcProgram, const char*) = nullptr;
+    nvrtcResult (*GetLoweredName)(nvrtcProgram, const char*, const char**) = nullptr;
+    const char* (*GetErrorString)(nvrtcResult) = nullptr;
+    /* driver */
+    CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
+    CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+                             CUstream, void**, void**) = nullptr;
+    CUresult (*Occupancy)(int*, CUfunction, int, size_t) = nullptr;
+    CUresult (*GetErrorName)(CUresult, const char**) = nullptr;
+};
+
+void* open_first(const std::vector<const char*>& names) {
+    for (const char* n : names)
+        if (void* h = dlopen(n, RTLD_NOW | RTLD_GLOBAL)) return h;
+    return nullptr;
+}
+
+Api& api() {
+    static Api a;
+    static std::once_flag once;
+    std::call_once(once, []() {
+        void* rtc = open_first({"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so"});
+        if (!rtc) {
+            a.why = "cannot load libnvrtc.so.12";
+            return;
+        }
+        void* drv = open_first({"libcuda.so.1", "libcuda.so"});
+        if (!drv) {
+            a.why = "cannot load libcuda.so.1 (no NVIDIA driver)";
+            return;
+        }
+#define L(h, field, sym)                                         \
+    a.field = (decltype(a.field))dlsym(h, sym);                  \
+    if (!a.field) {                                              \
+        a.why = std::string("missing symbol ") + sym;            \
+        return;                                                  \
+    }
+        L(rtc, CreateProgram, "nvrtcCreateProgram")
+        L(rtc, DestroyProgram, "nvrtcDestroyProgram")
+        L(rtc, CompileProgram, "nvrtcCompileProgram")
+        L(rtc, GetProgramLogSize, "nvrtcGetProgramLogSize")
+        L(rtc, GetProgramLog, "nvrtcGetProgramLog")
+        L(rtc, GetCUBINSize, "nvrtcGetCUBINSize")
+        L(rtc, GetCUBIN, "nvrtcGetCUBIN")
+        L(rtc, AddNameExpression, "nvrtcAddNameExpression")
+        L(rtc, GetLoweredName, "nvrtcGetLoweredName")
+        L(rtc, GetErrorString, "nvrtcGetErrorString")
+        L(drv, ModuleLoadData, "cuModuleLoadData")
+        L(drv, ModuleGetFunction, "cuModuleGetFunction")
+        L(drv, LaunchKernel, "cuLaunchKernel")
+        L(drv, Occupancy, "cuOccupancyMaxActiveBlocksPerMultiprocessor")
+        L(drv, GetErrorName, "cuGetErrorName")
+#undef L
+        a.ok = true;
+    });
+    return a;
+}
+
+std::mutex g_mu;
+std::vector<std::unique_ptr<JitSystem>> g_systems;
+
+struct Compiled {
+    CUmodule mod = nullptr;
+    CUfunction fn = nullptr;
+    int per_sm = 0;
+};
+/* (system, device, method, out_type) -> loaded kernel */
+std::map<std::tuple<int, int, int, int>, Compiled> g_cache;
+
+std::string stepper_expr(int method, int out_type) {
+    if (method == ODE_B200_RK4) return "ode_b200::Rk4Stepper<ode_b200::SysUser>";
+    if (method == ODE_B200_DOPRI5)
+        return "ode_b200::Dopri5Stepper<ode_b200::SysUser, " + std::to_string(out_type) + ">";
+    /* Dop853 treats Continuous like Sparse (dop853.rs:398,540-542) */
+    const int o = out_type == ODE_B200_OUT_DENSE ? ODE_B200_OUT_DENSE : ODE_B200_OUT_SPARSE;
+    return "ode_b200::Dop853Stepper<ode_b200::SysUser, " + std::to_string(o) + ">";
+}
+
+std::string make_source(const JitSystem& s, const std::string& stepper) {
+    std::string src = "#include \"ode_kernels.cuh\"\nnamespace ode_b200 {\nstruct SysUser {\n";
+    src += "  static constexpr int DIM = " + std::to_string(s.dim) + ", NP = " + std::to_string(s.n_params) + ";\n";
+    src += std::string("  static constexpr bool HAS_SOLOUT = ") + (s.has_solout ? "true" : "false") + ";\n";
+    src += "  ODE_DEV static void rhs(double x, const double* y, double* dy, const double* p) {\n" + s.rhs_body +
+           "\n  }\n";
+    src += "  ODE_DEV static bool solout(double x, const double* y, const double* dy, const double* p) {\n" +
+           (s.has_solout ? s.solout_body : std::string("return false;")) + "\n  }\n};\n}\n";
+    src += "template __global__ void ode_b200::ode_step_loop_kernel<" + stepper + " >(const ode_b200::KernelArgs);\n";
+    return src;
+}
+
+bool compile(const JitSystem& s, int method, int out_type, Compiled* out, std::string* err) {
+    Api& a = api();
+    const std::string stepper = stepper_expr(method, out_type);
+    const std::string src = make_source(s, stepper);
+    const std::string name_expr = "ode_b200::ode_step_loop_kernel<" + stepper + " >";
+    nvrtcProgram prog;
+    nvrtcResult r = a.CreateProgram(&prog, src.c_str(), (s.name + ".cu").c_str(), kNumEmbedded, kEmbeddedSources,
+                                    kEmbeddedNames);
+    if (r != NVRTC_SUCCESS) {
+        *err = std::string("nvrtcCreateProgram: ") + a.GetErrorString(r);
+        return false;
+    }
+    a.AddNameExpression(prog, name_expr.c_str());
+    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "-lineinfo",
+                          "-default-device"};
+    r = a.CompileProgram(prog, 5, opts);
+    if (r != NVRTC_SUCCESS) {
+        size_t n = 0;
+        a.GetProgramLogSize(prog, &n);
+        std::string log(n, '\0');
+        if (n) a.GetProgramLog(prog, &log[0]);
+        *err = std::string("NVRTC compile of system '") + s.name + "' failed: " + a.GetErrorString(r) + "\n" + log;
+        a.DestroyProgram(&prog);
+        return false;
+    }
+    const char* lowered = nullptr;
+    r = a.GetLoweredName(prog, name_expr.c_str(), &lowered);
+    if (r != NVRTC_SUCCESS || !lowered) {
+        *err = "nvrtcGetLoweredName failed";
+        a.DestroyProgram(&prog);
+        return false;
+    }
+    const std::string mangled = lowered;
+    size_t nbin = 0;
+    a.GetCUBINSize(prog, &nbin);
+    std::vector<char> bin(nbin);
+    r = a.GetCUBIN(prog, bin.data());
+    a.DestroyProgram(&prog);
+    if (r != NVRTC_SUCCESS || nbin == 0) {
+        *err = "nvrtcGetCUBIN failed";
+        return false;
+    }
+    CUresult cr = a.ModuleLoadData(&out->mod, bin.data());
+    if (cr == CUDA_SUCCESS) cr = a.ModuleGetFunction(&out->fn, out->mod, mangled.c_str());
+    if (cr != CUDA_SUCCESS) {
+        const char* nm = "?";
+        a.GetErrorName(cr, &nm);
+        *err = std::string("loading the JIT-compiled kernel failed: ") + nm;
+        return false;
+    }
+    return true;
+}
+
+}  // namespace
+
+int jit_register(const char* name, int dim, int n_params, const char* rhs_body, const char* solout_body,
+                 std::string* err) {
+    (void)err;
+    std::lock_guard<std::mutex> g(g_mu);
+    std::unique_ptr<JitSystem> s(new JitSystem());
+    s->name = name;
+    s->dim = dim;
+    s->n_params = n_params;
+    s->rhs_body = rhs_body;
+    s->has_solout = solout_body != nullptr && solout_body[0] != '\0';
+    if (s->has_solout) s->solout_body = solout_body;
+    g_systems.push_back(std::move(s));
+    return (int)g_systems.size() - 1;
+}
+
+const JitSystem* jit_system(int idx) {
+    std::lock_guard<std::mutex> g(g_mu);
+    if (idx < 0 || idx >= (int)g_systems.size()) return nullptr;
+    return g_systems[idx].get();
+}
+
+bool jit_launch(int idx, int device, int num_sms, int method, int out_type, const void* kernel_args,
+                size_t kernel_args_bytes, int block, long long blocks_all, int use_queue, void* stream,
+                std::string* err) {
+    (void)kernel_args_bytes;
+    Api& a = api();
+    if (!a.ok) {
+        *err = "JIT unavailable: " + a.why;
+        return false;
+    }
+    const JitSystem* s = jit_system(idx);
+    if (!s) {
+        *err = "bad JIT system index";
+        return false;
+    }
+    Compiled c;
+    {
+        std::lock_guard<std::mutex> g(g_mu);
+        const int o = method == ODE_B200_RK4 ? 0 : out_type;
+        auto key = std::make_tuple(idx, device, method, o);
+        auto it = g_cache.find(key);
+        if (it == g_cache.end()) {
+            if (!compile(*s, method, out_type, &c, err)) return false;
+            if (a.Occupancy(&c.per_sm, c.fn, block, 0) != CUDA_SUCCESS || c.per_sm < 1) {
+                *err = "JIT kernel does not fit on an SM";
+                return false;
+            }
+            g_cache[key] = c;
+        } else {
+            c = it->second;
+        }
+    }
+    long long grid = blocks_all;
+    if (use_queue) grid = std::min<long long>(blocks_all, (long long)num_sms * c.per_sm);
+    void* args[] = {const_cast<void*>(kernel_args)};
+    CUresult cr = a.LaunchKernel(c.fn, (unsigned)grid, 1, 1, (unsigned)block, 1, 1, 0, (CUstream)stream, args, nullptr);
+    if (cr != CUDA_SUCCESS) {
+        const char* nm = "?";
+        a.GetErrorName(cr, &nm);
+        *err = std::string("cuLaunchKernel failed: ") + nm;
+        return false;
+    }
+    return true;
+}
+
+}  // namespace ode_b200

@@ -1,0 +1,655 @@
+/*
+ * ode_kernels.cuh -- the hot path: persistent sm_100a step-loop kernels for Rk4, Dopri5 and
+ * Dop853, one trajectory per thread, state and stage vectors in registers.
+ *
+ * What each stepper restates (reference crate ode_solvers 0.6.1):
+ *   Rk4Stepper     src/rk4.rs:71-143      (integrate, step, populate_buffer)
+ *   Dopri5Stepper  src/dopri5.rs:263-495  (integrate_core, solution_output, compute_y_out)
+ *   Dop853Stepper  src/dop853.rs:254-559  (integrate, solution_output, compute_y_out)
+ * with Controller::accept (src/controller.rs:52-77) and hinit in ode_device.cuh.
+ *
+ * Bit-parity rules followed everywhere:
+ *  - operation order exactly as the Rust source evaluates it (left-associated nalgebra
+ *    expressions, one rounding per operation, no FMA: compiled with -fmad=false);
+ *  - tableau coefficients are compile-time immediates; terms whose coefficient is a
+ *    structural zero are skipped (x + k*0.0 == x for finite k). To keep the reference's
+ *    behaviour when a stage derivative is inf/NaN (there inf*0.0 = NaN poisons the error
+ *    estimate and the step is rejected), every stage output is tested with an integer-pipe
+ *    exponent check and a hit forces err = NaN, i.e. the same reject + h/facc1 shrink;
+ *  - identical sub-expressions the source evaluates twice ((e/sc)*(e/sc), k*h) are computed
+ *    once: same operands, same rounding, same bits.
+ */
+#pragma once
+
+#include "ode_device.cuh"
+
+namespace ode_b200 {
+
+
+
+/* ============================================================================ Rk4 */
+template <class Sys>
+struct Rk4Stepper {
+    static constexpr int N = Sys::DIM;
+    struct State {
+        double y[N];
+        double p[Sys::NP > 0 ? Sys::NP : 1];
+        double x;
+        unsigned long long steps_left;
+        Counters c;
+        long long traj;
+        int status;
+    };
+
+    /* Rk4::integrate prologue, rk4.rs:71-77 */
+    ODE_DEV static void init(State& s, const KernelArgs& a, long long t) {
+        s.traj = t;
+        load_traj_<Sys>(a, t, s.y, s.p);
+        s.x = a.cfg.x0;
+        counters_init_(s.c);
+        s.status = ODE_B200_OK;
+        push_<N>(a, t, s.c.out_count, s.x, s.y);
+        const double ns = ceil((a.cfg.x_end - s.x) / a.cfg.step_size);
+        if (!(ns >= 0.0) || ns > 4.0e9) { /* to_usize().unwrap() panics in the reference */
+            s.status = ODE_B200_UNSUPPORTED_DOMAIN;
+            s.steps_left = 0;
+        } else {
+            s.steps_left = (unsigned long long)ns;
+        }
+    }
+
+    /* one Rk4::step + the loop body of integrate, rk4.rs:79-98,103-132 */
+    ODE_DEV static bool attempt(State& s, const KernelArgs& a) {
+        if (s.steps_left == 0) {
+            store_final_<N>(a, s.traj, s.y, s.x, a.cfg.step_size, s.c, s.status, 0.0);
+            return true;
+        }
+        const double step = a.cfg.step_size, half = step / 2.0, x = s.x;
+        double k0[N], k1[N], k2[N], k3[N], buf[N], yn[N];
+        Sys::rhs(x, s.y, k0, s.p);
+#pragma unroll
+        for (int i = 0; i < N; ++i) buf[i] = s.y[i] + k0[i] * half;
+        Sys::rhs(x + half, buf, k1, s.p);
+#pragma unroll
+        for (int i = 0; i < N; ++i) buf[i] = s.y[i] + k1[i] * half;
+        Sys::rhs(x + half, buf, k2, s.p);
+#pragma unroll
+        for (int i = 0; i < N; ++i) buf[i] = s.y[i] + k2[i] * step;
+        Sys::rhs(x + step, buf, k3, s.p);
+        const double x_new = x + step;
+        const double h6 = step / 6.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) yn[i] = s.y[i] + (((k0[i] + k1[i] * 2.0) + k2[i] * 2.0) + k3[i]) * h6;
+        bool stop = false;
+        if constexpr (Sys::HAS_SOLOUT) stop = Sys::solout(x_new, yn, k0, s.p);
+        s.x = x_new;
+#pragma unroll
+        for (int i = 0; i < N; ++i) s.y[i] = yn[i];
+        push_<N>(a, s.traj, s.c.out_count, x_new, yn);
+        s.c.num_eval += 4;
+        s.c.accepted += 1;
+        s.c.n_step += 1;
+        s.steps_left -= 1;
+        if (stop) s.steps_left = 0;
+        if (s.steps_left == 0) {
+            store_final_<N>(a, s.traj, s.y, s.x, step, s.c, s.status, 0.0);
+            return true;
+        }
+        return false;
+    }
+};
+
+/* ============================================================================ Dopri5 */
+template <class Sys, int OUT>
+struct Dopri5Stepper {
+    static constexpr int N = Sys::DIM;
+    static constexpr bool DENSE = OUT == ODE_B200_OUT_DENSE;
+    static constexpr bool CONT = OUT == ODE_B200_OUT_CONTINUOUS;
+    static constexpr bool TRACK_LAST = DENSE && Sys::HAS_SOLOUT;
+
+    struct State {
+        double y[N], k0[N]; /* k0 = f(x, y): first-same-as-last slot k[0] */
+        double p[Sys::NP > 0 ? Sys::NP : 1];
+        double ylast[TRACK_LAST ? N : 1]; /* results.last() (only solout reads it) */
+        double x, h, x_old, h_old, xd;
+        CtrlState ctrl;
+        Counters c;
+        unsigned iasti, non_stiff, stiff_ctr;
+        long long traj;
+    };
+
+    ODE_DEV static bool finish(State& s, const KernelArgs& a, int status) {
+        store_final_<N>(a, s.traj, s.y, s.x, s.h_old, s.c, status, a.cfg.x0);
+        return true;
+    }
+
+    /* integrate_core prologue, dopri5.rs:268-296 */
+    ODE_DEV static void init(State& s, const KernelArgs& a, long long t) {
+        s.traj = t;
+        load_traj_<Sys>(a, t, s.y, s.p);
+        s.x = s.x_old = s.xd = a.cfg.x0;
+        counters_init_(s.c);
+        ctrl_init_(s.ctrl);
+        s.iasti = s.non_stiff = s.stiff_ctr = 0;
+        s.h = a.cfg.h0;
+        if (s.h == 0.0) {
+            s.h = hinit_<Sys>(a, s.x, s.y, s.p, 1.0 / 5.0);
+            s.c.num_eval += 2;
+        }
+        s.h_old = s.h;
+        if constexpr (OUT == ODE_B200_OUT_SPARSE) push_<N>(a, t, s.c.out_count, s.x, s.y);
+        Sys::rhs(s.x, s.y, s.k0, s.p);
+        s.c.num_eval += 1;
+    }
+
+    /* compute_y_out, dopri5.rs:490-495 */
+    ODE_DEV static void y_out(const double (&rc)[5][N], double th, double th1, double (&o)[N]) {
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            o[i] = rc[0][i] + (rc[1][i] + (rc[2][i] + (rc[3][i] + rc[4][i] * th1) * th) * th1) * th;
+    }
+
+    /* one pass of `while !last`, dopri5.rs:299-443 */
+    ODE_DEV static bool attempt(State& s, const KernelArgs& a) {
+        const ode_b200_config& cfg = a.cfg;
+        if (s.c.n_step > cfg.n_max) { /* '>' here, '>=' in dop853 (Q2) */
+            s.h_old = s.h;
+            return finish(s, a, ODE_B200_MAX_NUM_STEP_REACHED);
+        }
+        if (0.1 * fabs(s.h) <= cfg.uround * fabs(s.x)) {
+            s.h_old = s.h;
+            return finish(s, a, ODE_B200_STEP_SIZE_UNDERFLOW);
+        }
+        bool last = false;
+        if ((s.x + 1.01 * s.h - cfg.x_end) * a.posneg > 0.0) {
+            s.h = cfg.x_end - s.x;
+            last = true;
+        }
+        s.c.n_step += 1;
+        const double h = s.h, x = s.x;
+
+        /* 6 stages, dopri5.rs:326-340. k[s] for s = 1..6; k[6] is the reference's new k[1]. */
+        double k[7][N], ynext[N], ystiff[N];
+        bool bad = false;
+#pragma unroll
+        for (int i = 0; i < N; ++i) k[0][i] = s.k0[i];
+        static_for<1, 7>([&](auto S) {
+            constexpr int sg = decltype(S)::value;
+#pragma unroll
+            for (int i = 0; i < N; ++i) ynext[i] = s.y[i];
+            static_for<0, sg>([&](auto J) {
+                constexpr int j = decltype(J)::value;
+                constexpr double aij = TabDp5::a(sg, j);
+                if constexpr (aij != 0.0) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) ynext[i] = ynext[i] + (k[j][i] * h) * aij;
+                }
+            });
+            Sys::rhs(x + h * TabDp5::c(sg), ynext, k[sg], s.p);
+#pragma unroll
+            for (int i = 0; i < N; ++i) bad |= nonfinite_(k[sg][i]);
+            if constexpr (sg == 5) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) ystiff[i] = ynext[i];
+            }
+        });
+        s.c.num_eval += 6;
+
+        /* error estimate and norm, dopri5.rs:354-371 */
+        double err = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double ee = (((((k[0][i] * TabDp5::e(0) + k[2][i] * TabDp5::e(2)) + k[3][i] * TabDp5::e(3)) +
+                                 k[4][i] * TabDp5::e(4)) +
+                                k[5][i] * TabDp5::e(5)) +
+                               k[6][i] * TabDp5::e(6)) *
+                              h;
+            const double sc = cfg.atol + fmax(fabs(s.y[i]), fabs(ynext[i])) * cfg.rtol;
+            const double q = ee / sc;
+            err += q * q;
+        }
+        err = sqrt(err / (double)N);
+        if (bad) err = qnan_();
+
+        double h_new;
+        if (ctrl_accept_(s.ctrl, a, err, h, h_new)) {
+            s.c.accepted += 1;
+            /* stiffness detection, dopri5.rs:378-402 (accepted % n_stiff == 0 kept as a counter) */
+            if (++s.stiff_ctr == cfg.n_stiff) s.stiff_ctr = 0;
+            if (s.stiff_ctr == 0 || s.iasti > 0) {
+                const double num = diff_dot_<N>(k[6], k[5]);
+                const double den = diff_dot_<N>(ynext, ystiff);
+                const double h_lamb = den > 0.0 ? h * sqrt(num / den) : 0.0;
+                if (h_lamb > 3.25) {
+                    s.iasti += 1;
+                    s.non_stiff = 0;
+                    if (s.iasti == 15) {
+                        s.h_old = h;
+                        return finish(s, a, ODE_B200_STIFFNESS_DETECTED);
+                    }
+                } else {
+                    s.non_stiff += 1;
+                    if (s.non_stiff == 6) s.iasti = 0;
+                }
+            }
+            /* dense / continuous coefficients, dopri5.rs:343-351 (rcont[4], computed by the
+             * reference on every attempt but only read after an accept) and :405-414 */
+            double rc[5][N];
+            if constexpr (DENSE || CONT) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    rc[4][i] = (((((k[0][i] * TabDp5::d(0) + k[2][i] * TabDp5::d(2)) + k[3][i] * TabDp5::d(3)) +
+                                  k[4][i] * TabDp5::d(4)) +
+                                 k[5][i] * TabDp5::d(5)) +
+                                k[6][i] * TabDp5::d(6)) *
+                               h;
+                    const double ydiff = ynext[i] - s.y[i];
+                    const double bspl = k[0][i] * h - ydiff;
+                    rc[0][i] = s.y[i];
+                    rc[1][i] = ydiff;
+                    rc[2][i] = bspl;
+                    rc[3][i] = ((-k[6][i]) * h + ydiff) - bspl;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                s.k0[i] = k[6][i];
+                s.y[i] = ynext[i];
+            }
+            s.x_old = x;
+            s.x = x + h;
+            s.h_old = h;
+
+            /* solution_output, dopri5.rs:447-487 */
+            bool stop = false;
+            if constexpr (DENSE) {
+                bool unsupported = false;
+                double yo[N];
+                while (fabs(s.xd) <= fabs(s.x)) {
+                    bool pushed = false;
+                    if (fabs(s.x_old) <= fabs(s.xd) && fabs(s.x) >= fabs(s.xd)) {
+                        const double th = (s.xd - s.x_old) / s.h_old, th1 = 1.0 - th;
+                        y_out(rc, th, th1, yo);
+                        push_<N>(a, s.traj, s.c.out_count, s.xd, yo);
+                        if constexpr (TRACK_LAST) {
+#pragma unroll
+                            for (int i = 0; i < N; ++i) s.ylast[i] = yo[i];
+                        }
+                        s.xd += cfg.dx;
+                        pushed = true;
+                    }
+                    if (s.c.out_count == 0) { unsupported = true; break; } /* reference: unwrap() on empty */
+                    if constexpr (Sys::HAS_SOLOUT) {
+                        if (Sys::solout(s.xd, s.ylast, s.k0, s.p)) break;
+                    }
+                    if (!pushed || s.c.out_count > (1u << 30)) { unsupported = true; break; } /* reference never returns */
+                }
+                if (unsupported) return finish(s, a, ODE_B200_UNSUPPORTED_DOMAIN);
+                if (fabs(s.xd - cfg.x_end) < 1.0e-9) { /* endpoint rule, dopri5.rs:472-478 (Q9) */
+                    const double th = (cfg.x_end - s.x_old) / s.h_old, th1 = 1.0 - th;
+                    y_out(rc, th, th1, yo);
+                    push_<N>(a, s.traj, s.c.out_count, cfg.x_end, yo);
+                    if constexpr (TRACK_LAST) {
+#pragma unroll
+                        for (int i = 0; i < N; ++i) s.ylast[i] = yo[i];
+                    }
+                    s.xd += cfg.dx;
+                }
+                if (s.c.out_count == 0) return finish(s, a, ODE_B200_UNSUPPORTED_DOMAIN);
+                if constexpr (Sys::HAS_SOLOUT) stop = Sys::solout(s.x, s.ylast, s.k0, s.p);
+            } else {
+                push_<N>(a, s.traj, s.c.out_count, s.x, s.y);
+                if constexpr (CONT) { /* add_interval(|x|, rcont, h_old), dopri5.rs:484-486 */
+                    const ode_b200_outputs& o = a.out;
+                    if (o.com_break != nullptr && (long long)s.c.com_count < o.com_cap) {
+                        const size_t q = (size_t)s.traj * (size_t)o.com_cap + s.c.com_count;
+                        o.com_break[q] = fabs(s.x);
+                        o.com_step[q] = s.h_old;
+#pragma unroll
+                        for (int r = 0; r < 5; ++r)
+#pragma unroll
+                            for (int i = 0; i < N; ++i) o.com_coef[(q * 5 + r) * N + i] = rc[r][i];
+                    }
+                    s.c.com_count += 1;
+                }
+                if constexpr (Sys::HAS_SOLOUT) stop = Sys::solout(s.x, s.y, s.k0, s.p);
+            }
+            if (stop) last = true;
+            if (last) { /* normal exit, dopri5.rs:432-435 */
+                s.h_old = a.posneg * h_new;
+                return finish(s, a, ODE_B200_OK);
+            }
+        } else {
+            if (s.c.accepted >= 1) s.c.rejected += 1; /* Q5 */
+        }
+        s.h = h_new;
+        return false;
+    }
+};
+
+/* ============================================================================ Dop853 */
+/* OUT: Dense, or Sparse (the reference treats Continuous like Sparse: dop853.rs:398,540-542) */
+template <class Sys, int OUT>
+struct Dop853Stepper {
+    static constexpr int N = Sys::DIM;
+    static constexpr bool DENSE = OUT == ODE_B200_OUT_DENSE;
+    static constexpr bool TRACK_LAST = DENSE && Sys::HAS_SOLOUT;
+
+    struct State {
+        double y[N], k0[N]; /* k0 = reference k[0] = f(x, y) */
+        double p[Sys::NP > 0 ? Sys::NP : 1];
+        double ylast[TRACK_LAST ? N : 1];
+        double x, h, x_old, h_old, xd;
+        CtrlState ctrl;
+        Counters c;
+        unsigned iasti, non_stiff, stiff_ctr;
+        long long traj;
+    };
+
+    ODE_DEV static bool finish(State& s, const KernelArgs& a, int status) {
+        store_final_<N>(a, s.traj, s.y, s.x, s.h_old, s.c, status, 0.0);
+        return true;
+    }
+
+    /* compute_y_out, dop853.rs:546-559 */
+    ODE_DEV static void y_out(const double (&rc)[8][N], double th, double th1, double (&o)[N]) {
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            o[i] = rc[0][i] +
+                   (rc[1][i] +
+                    (rc[2][i] +
+                     (rc[3][i] + (rc[4][i] + (rc[5][i] + (rc[6][i] + rc[7][i] * th) * th1) * th) * th1) * th) *
+                        th1) *
+                       th;
+    }
+
+    /* integrate prologue, dop853.rs:255-278 */
+    ODE_DEV static void init(State& s, const KernelArgs& a, long long t) {
+        s.traj = t;
+        load_traj_<Sys>(a, t, s.y, s.p);
+        s.x = s.x_old = s.xd = a.cfg.x0;
+        counters_init_(s.c);
+        ctrl_init_(s.ctrl);
+        s.iasti = s.non_stiff = s.stiff_ctr = 0;
+        s.h = a.cfg.h0;
+        if (s.h == 0.0) {
+            s.h = hinit_<Sys>(a, s.x, s.y, s.p, 0.125);
+            s.c.num_eval += 2;
+        }
+        s.h_old = s.h;
+        /* solution_output(y0), dop853.rs:273-274 -> :515-519 / :541 */
+        if constexpr (DENSE) {
+            /* first call: |xd - x0| = 0 < EPSILON always */
+            push_<N>(a, t, s.c.out_count, a.cfg.x0, s.y);
+            if constexpr (TRACK_LAST) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) s.ylast[i] = s.y[i];
+            }
+            s.xd += a.cfg.dx;
+        } else {
+            push_<N>(a, t, s.c.out_count, a.cfg.x0, s.y);
+        }
+        Sys::rhs(s.x, s.y, s.k0, s.p);
+        s.c.num_eval += 1;
+    }
+
+    /* one pass of `while !last`, dop853.rs:281-510 */
+    ODE_DEV static bool attempt(State& s, const KernelArgs& a) {
+        const ode_b200_config& cfg = a.cfg;
+        if (s.c.n_step >= cfg.n_max) { /* '>=' (Q2) */
+            s.h_old = s.h;
+            return finish(s, a, ODE_B200_MAX_NUM_STEP_REACHED);
+        }
+        if (0.1 * fabs(s.h) <= cfg.uround * fabs(s.x)) {
+            s.h_old = s.h;
+            return finish(s, a, ODE_B200_STEP_SIZE_UNDERFLOW);
+        }
+        bool last = false;
+        if ((s.x + 1.01 * s.h - cfg.x_end) * a.posneg > 0.0) {
+            s.h = cfg.x_end - s.x;
+            last = true;
+        }
+        s.c.n_step += 1;
+        const double h = s.h, x = s.x;
+
+        /* stages 2..12, dop853.rs:307-321: k[s] = f(x + h*c(s+1), y + sum_j k[j]*(h*a(s+1,j+1))) */
+        double k[12][N], ynext[N];
+        bool bad = false;
+#pragma unroll
+        for (int i = 0; i < N; ++i) k[0][i] = s.k0[i];
+        static_for<1, 12>([&](auto S) {
+            constexpr int sg = decltype(S)::value;
+#pragma unroll
+            for (int i = 0; i < N; ++i) ynext[i] = s.y[i];
+            static_for<0, sg>([&](auto J) {
+                constexpr int j = decltype(J)::value;
+                constexpr double aij = TabDp8::a(sg, j);
+                if constexpr (aij != 0.0) {
+                    const double ha = h * aij;
+#pragma unroll
+                    for (int i = 0; i < N; ++i) ynext[i] = ynext[i] + k[j][i] * ha;
+                }
+            });
+            Sys::rhs(x + (h * TabDp8::c(sg)), ynext, k[sg], s.p); /* c(12) = 0.0 (Q1) */
+#pragma unroll
+            for (int i = 0; i < N; ++i) bad |= nonfinite_(k[sg][i]);
+        });
+        s.c.num_eval += 11;
+        /* from here the reference's slots are: k[1] = k11 (our k[10]), k[2] = k12 (our k[11]) */
+
+        /* 8th-order solution, dop853.rs:323-331 */
+        double bsum[N], y8[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            bsum[i] = ((((((k[0][i] * TabDp8::b(0) + k[5][i] * TabDp8::b(5)) + k[6][i] * TabDp8::b(6)) +
+                          k[7][i] * TabDp8::b(7)) +
+                         k[8][i] * TabDp8::b(8)) +
+                        k[9][i] * TabDp8::b(9)) +
+                       k[10][i] * TabDp8::b(10)) +
+                      k[11][i] * TabDp8::b(11);
+            y8[i] = s.y[i] + bsum[i] * h;
+        }
+        /* error estimators and norm, dop853.rs:334-362. err_est runs over the 12 slots; slots
+         * 1..4 (k11, k12, bsum, y8) meet e2..e5 = 0 and are skipped. */
+        double err = 0.0, err2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double ee = k[0][i] * TabDp8::e(0); /* 0.0 + v == v */
+            ee = ee + k[5][i] * TabDp8::e(5);
+            ee = ee + k[6][i] * TabDp8::e(6);
+            ee = ee + k[7][i] * TabDp8::e(7);
+            ee = ee + k[8][i] * TabDp8::e(8);
+            ee = ee + k[9][i] * TabDp8::e(9);
+            ee = ee + k[10][i] * TabDp8::e(10);
+            ee = ee + k[11][i] * TabDp8::e(11);
+            const double eb = ((bsum[i] - k[0][i] * TabDp8::bhh(0)) - k[8][i] * TabDp8::bhh(1)) -
+                              k[11][i] * TabDp8::bhh(2);
+            const double sc = cfg.atol + fmax(fabs(s.y[i]), fabs(y8[i])) * cfg.rtol;
+            const double q1 = ee / sc, q2 = eb / sc;
+            err += q1 * q1;
+            err2 += q2 * q2;
+        }
+        double deno = err + 0.01 * err2;
+        if (deno <= 0.0) deno = 1.0;
+        err = fabs(h) * err * sqrt(1.0 / (deno * (double)N));
+        if (bad) err = qnan_();
+
+        double h_new;
+        if (ctrl_accept_(s.ctrl, a, err, h, h_new)) {
+            s.c.accepted += 1;
+            double knew[N]; /* reference k[3] = f(x + h, k[4]); no FSAL reuse (Q11) */
+            Sys::rhs(x + h, y8, knew, s.p);
+            s.c.num_eval += 1;
+
+            /* stiffness detection, dop853.rs:372-396 */
+            if (++s.stiff_ctr == cfg.n_stiff) s.stiff_ctr = 0;
+            if (s.stiff_ctr == 0 || s.iasti > 0) {
+                const double num = diff_dot_<N>(knew, k[11]);
+                const double den = diff_dot_<N>(y8, ynext); /* ynext = argument of stage 12 */
+                const double h_lamb = den > 0.0 ? h * sqrt(num / den) : 0.0;
+                if (h_lamb > 6.1) {
+                    s.non_stiff = 0;
+                    s.iasti += 1;
+                    if (s.iasti == 15) {
+                        s.h_old = h;
+                        return finish(s, a, ODE_B200_STIFFNESS_DETECTED);
+                    }
+                } else {
+                    s.non_stiff += 1;
+                    if (s.non_stiff == 6) s.iasti = 0;
+                }
+            }
+
+            double rc[8][N];
+            if constexpr (DENSE) { /* dop853.rs:398-480 */
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    rc[0][i] = s.y[i];
+                    const double ydiff = y8[i] - s.y[i];
+                    rc[1][i] = ydiff;
+                    const double bspl = k[0][i] * h - ydiff;
+                    rc[2][i] = bspl;
+                    rc[3][i] = (ydiff - knew[i] * h) - bspl;
+                }
+                /* rcont[4..7] = sum_{j=1..12} slot[j-1]*d(i,j): columns 2..5 are zero; slot 10/11 = k11/k12 */
+                static_for<0, 4>([&](auto R) {
+                    constexpr int r = decltype(R)::value;
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        double v = k[0][i] * TabDp8::d(r, 0);
+                        v = v + k[5][i] * TabDp8::d(r, 5);
+                        v = v + k[6][i] * TabDp8::d(r, 6);
+                        v = v + k[7][i] * TabDp8::d(r, 7);
+                        v = v + k[8][i] * TabDp8::d(r, 8);
+                        v = v + k[9][i] * TabDp8::d(r, 9);
+                        v = v + k[10][i] * TabDp8::d(r, 10);
+                        v = v + k[11][i] * TabDp8::d(r, 11);
+                        rc[4 + r][i] = v;
+                    }
+                });
+                /* the three extra stages 14, 15, 16 (dop853.rs:414-454) */
+                double yy[N], k14[N], k15[N], k16[N];
+#pragma unroll
+                for (int i = 0; i < N; ++i)
+                    yy[i] = s.y[i] + (((((((k[0][i] * TabDp8::a(13, 0) + k[6][i] * TabDp8::a(13, 6)) +
+                                            k[7][i] * TabDp8::a(13, 7)) +
+                                           k[8][i] * TabDp8::a(13, 8)) +
+                                          k[9][i] * TabDp8::a(13, 9)) +
+                                         k[10][i] * TabDp8::a(13, 10)) +
+                                        k[11][i] * TabDp8::a(13, 11)) +
+                                       knew[i] * TabDp8::a(13, 12)) *
+                                          h;
+                Sys::rhs(x + h * TabDp8::c(13), yy, k14, s.p);
+#pragma unroll
+                for (int i = 0; i < N; ++i)
+                    yy[i] = s.y[i] + (((((((k[0][i] * TabDp8::a(14, 0) + k[5][i] * TabDp8::a(14, 5)) +
+                                            k[6][i] * TabDp8::a(14, 6)) +
+                                           k[7][i] * TabDp8::a(14, 7)) +
+                                          k[10][i] * TabDp8::a(14, 10)) +
+                                         k[11][i] * TabDp8::a(14, 11)) +
+                                        knew[i] * TabDp8::a(14, 12)) +
+                                       k14[i] * TabDp8::a(14, 13)) *
+                                          h;
+                Sys::rhs(x + h * TabDp8::c(14), yy, k15, s.p);
+#pragma unroll
+                for (int i = 0; i < N; ++i)
+                    yy[i] = s.y[i] + (((((((k[0][i] * TabDp8::a(15, 0) + k[5][i] * TabDp8::a(15, 5)) +
+                                            k[6][i] * TabDp8::a(15, 6)) +
+                                           k[7][i] * TabDp8::a(15, 7)) +
+                                          k[8][i] * TabDp8::a(15, 8)) +
+                                         knew[i] * TabDp8::a(15, 12)) +
+                                        k14[i] * TabDp8::a(15, 13)) +
+                                       k15[i] * TabDp8::a(15, 14)) *
+                                          h;
+                Sys::rhs(x + h * TabDp8::c(15), yy, k16, s.p);
+                s.c.num_eval += 3;
+                static_for<0, 4>([&](auto R) {
+                    constexpr int r = decltype(R)::value;
+#pragma unroll
+                    for (int i = 0; i < N; ++i)
+                        rc[4 + r][i] = ((((rc[4 + r][i] + knew[i] * TabDp8::d(r, 12)) + k14[i] * TabDp8::d(r, 13)) +
+                                         k15[i] * TabDp8::d(r, 14)) +
+                                        k16[i] * TabDp8::d(r, 15)) *
+                                       h;
+                });
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                s.k0[i] = knew[i];
+                s.y[i] = y8[i];
+            }
+            s.x_old = x;
+            s.x = x + h;
+            s.h_old = h;
+
+            /* solution_output(k[4]), dop853.rs:515-543 */
+            if constexpr (DENSE) {
+                double yo[N];
+                if (fabs(s.xd - cfg.x0) < 2.220446049250313e-16) {
+                    push_<N>(a, s.traj, s.c.out_count, cfg.x0, s.y);
+                    if constexpr (TRACK_LAST) {
+#pragma unroll
+                        for (int i = 0; i < N; ++i) s.ylast[i] = s.y[i];
+                    }
+                    s.xd += cfg.dx;
+                } else {
+                    bool unsupported = false;
+                    while (fabs(s.xd) <= fabs(s.x)) {
+                        if (fabs(s.x_old) <= fabs(s.xd) && fabs(s.x) >= fabs(s.xd)) {
+                            const double th = (s.xd - s.x_old) / s.h_old, th1 = 1.0 - th;
+                            y_out(rc, th, th1, yo);
+                            push_<N>(a, s.traj, s.c.out_count, s.xd, yo);
+                            if constexpr (TRACK_LAST) {
+#pragma unroll
+                                for (int i = 0; i < N; ++i) s.ylast[i] = yo[i];
+                            }
+                            s.xd += cfg.dx;
+                            if (s.c.out_count > (1u << 30)) { unsupported = true; break; }
+                        } else { /* the reference never leaves this loop */
+                            unsupported = true;
+                            break;
+                        }
+                    }
+                    if (unsupported) return finish(s, a, ODE_B200_UNSUPPORTED_DOMAIN);
+                    if (fabs(s.xd - cfg.x_end) < 1.0e-9) {
+                        const double th = (cfg.x_end - s.x_old) / s.h_old, th1 = 1.0 - th;
+                        y_out(rc, th, th1, yo);
+                        push_<N>(a, s.traj, s.c.out_count, cfg.x_end, yo);
+                        if constexpr (TRACK_LAST) {
+#pragma unroll
+                            for (int i = 0; i < N; ++i) s.ylast[i] = yo[i];
+                        }
+                        s.xd += cfg.dx;
+                    }
+                }
+            } else {
+                push_<N>(a, s.traj, s.c.out_count, cfg.x0, s.y); /* pushes x0, not x (Q6) */
+            }
+
+            bool stop = false;
+            if constexpr (Sys::HAS_SOLOUT) {
+                if constexpr (DENSE)
+                    stop = Sys::solout(s.x, s.ylast, s.k0, s.p);
+                else
+                    stop = Sys::solout(s.x, s.y, s.k0, s.p);
+            }
+            if (stop) last = true;
+            if (last) { /* dop853.rs:499-502 */
+                s.h_old = a.posneg * h_new;
+                return finish(s, a, ODE_B200_OK);
+            }
+        } else {
+            if (s.c.accepted >= 1) s.c.rejected += 1;
+        }
+        s.h = h_new;
+        return false;
+    }
+};
+
+/* ============================================================================ kernels */
+template <class Stepper>
+__global__ void __launch_bounds__(kBlockThreads) ode_step_loop_kernel(const __grid_constant__ KernelArgs a) {
+    run_lanes_<Stepper>(a);
+}
+
+}  // namespace ode_b200

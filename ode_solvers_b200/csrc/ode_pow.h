@@ -194,7 +194,7 @@ ODE_POW_SLOW int ode_pow_special_(double x, double y, ode_u64* pix, ode_u32* psi
             *res = ix > 0x3ff0000000000000ULL ? 1.0 + y : 1.0 - y;
             return 1;
         }
-        *res = ((ix > 0x3ff0000000000000ULL) == (topy < 0x800u)) ? (0x1p769 * 0x1p769) : (0x1p-767 * 0x1p-767);
+        *res = ((ix > 0x3ff0000000000000ULL) == (topy < 0x800u)) ? ODE_ASF64(0x7ff0000000000000ULL) : 0.0; /* __math_oflow(0) : __math_uflow(0) */
         return 1;
     }
     if (topx == 0) { /* subnormal x: normalise */

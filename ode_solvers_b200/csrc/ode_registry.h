@@ -1,0 +1,18 @@
+/*
+ * ode_registry.h -- host-side table of compiled systems: for every (method, out_type) the
+ * address of the matching ode_step_loop_kernel instantiation.
+ */
+#pragma once
+
+namespace ode_b200 {
+
+struct SystemEntry {
+    const char* name;
+    int dim;
+    int n_params;
+    int has_solout;
+    /* [method: Rk4, Dopri5, Dop853][out_type: Dense, Sparse, Continuous] */
+    const void* kernels[3][3];
+};
+
+}  // namespace ode_b200

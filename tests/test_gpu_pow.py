@@ -1,0 +1,74 @@
+"""Device pow()/exp() clones must be BIT-identical to the host libm the reference's
+f64::powf / f64::exp resolve to (controller.rs:53-54, dopri5.rs:236, dop853.rs:244)."""
+import numpy as np
+import pytest
+
+import ode_solvers_b200 as ob
+import oracle
+from ode_solvers_b200 import _abi
+from parity_util import same_f64
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev_pow(x, y):
+    lib = _abi.load()
+    ctx = ob.default_context(0)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(np.broadcast_to(y, x.shape), dtype=np.float64)
+    out = np.zeros_like(x)
+    assert lib.ode_b200_debug_pow(ctx.handle, x.size, x.ctypes.data, y.ctypes.data, out.ctypes.data) == 0
+    return out
+
+
+def _dev_exp(x):
+    lib = _abi.load()
+    ctx = ob.default_context(0)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.zeros_like(x)
+    assert lib.ode_b200_debug_exp(ctx.handle, x.size, x.ctypes.data, out.ctypes.data) == 0
+    return out
+
+
+def _libm_pow(x, y):
+    y = np.broadcast_to(y, np.shape(x))
+    f = oracle.lib().ode_oracle_pow
+    return np.array([f(float(a), float(b)) for a, b in zip(np.ravel(x), np.ravel(y))]).reshape(np.shape(x))
+
+
+def _libm_exp(x):
+    f = oracle.lib().ode_oracle_exp
+    return np.array([f(float(a)) for a in np.ravel(x)]).reshape(np.shape(x))
+
+
+def test_pow_controller_domain():
+    rng = np.random.default_rng(3)
+    n = 200_000
+    for a in (0.2 - 0.04 * 0.75, 0.125, -0.04, 0.2):
+        x = 10 ** rng.uniform(-8, 2, n)
+        assert same_f64(_dev_pow(x, a), _libm_pow(x, a)).all()
+
+
+def test_pow_wide_and_special():
+    rng = np.random.default_rng(4)
+    n = 200_000
+    x = 10 ** rng.uniform(-320, 308, n)
+    y = rng.uniform(-3, 3, n)
+    assert same_f64(_dev_pow(x, y), _libm_pow(x, y)).all()
+    x = rng.uniform(-10, 10, n)
+    y = rng.integers(-8, 9, n).astype(float)
+    assert same_f64(_dev_pow(x, y), _libm_pow(x, y)).all()
+    sp = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 5e-324, 2.2e-308, 1.7e308, 0.5, 2.0, 3.0, -3.0,
+                   1e-70, 1e70, 9e18, 1e19])
+    X, Y = np.meshgrid(sp, sp)
+    assert same_f64(_dev_pow(X.ravel(), Y.ravel()), _libm_pow(X.ravel(), Y.ravel())).all()
+    x = np.exp(rng.uniform(-2, 2, n))
+    y = rng.uniform(-600, 600, n)
+    assert same_f64(_dev_pow(x, y), _libm_pow(x, y)).all()
+
+
+def test_exp():
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.uniform(-5, 5, 200_000), rng.uniform(-750, 720, 200_000),
+                        [0.0, -0.0, np.inf, -np.inf, np.nan, 1e-20, -1e-20, 709.78, 709.79, -745.1, -745.2]])
+    assert same_f64(_dev_exp(x), _libm_exp(x)).all()
