@@ -180,6 +180,8 @@ void          ode_b200_destroy(ode_b200_ctx*);
 double        ode_b200_last_kernel_ms(const ode_b200_ctx*);
 /* number of kernel launches issued by this context since creation */
 uint64_t      ode_b200_launch_count(const ode_b200_ctx*);
+/* the context's own stream (cudaStream_t as void*) */
+void*         ode_b200_stream(const ode_b200_ctx*);
 
 /* ---- the hot path ---------------------------------------------------------------- */
 /*
@@ -193,8 +195,9 @@ int ode_b200_integrate_batch(ode_b200_ctx* ctx, int sys_id, const ode_b200_confi
                              int params_per_traj, const ode_b200_outputs* out);
 /*
  * Device-buffer entry: same, but every pointer (y0, params, all of *out) is device memory
- * on the context's GPU and the kernel is enqueued on `cuda_stream` (a cudaStream_t; NULL =
- * the context's own stream) without synchronising.
+ * on the context's GPU and the kernel is enqueued on `cuda_stream` (a cudaStream_t passed as
+ * void*; NULL = the CUDA default stream, as everywhere in CUDA) without synchronising.
+ * ode_b200_stream(ctx) returns the context's own non-blocking stream.
  */
 int ode_b200_integrate_batch_device(ode_b200_ctx* ctx, int sys_id, const ode_b200_config* cfg,
                                     int64_t n_traj, const double* y0, const double* params,

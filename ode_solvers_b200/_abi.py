@@ -115,6 +115,7 @@ ABI_SYMBOLS = [
     "ode_b200_system_name", "ode_b200_system_from_source",
     "ode_b200_config_new", "ode_b200_config_from_param", "ode_b200_config_rk4",
     "ode_b200_create", "ode_b200_destroy", "ode_b200_last_kernel_ms", "ode_b200_launch_count",
+    "ode_b200_stream",
     "ode_b200_integrate_batch", "ode_b200_integrate_batch_device", "ode_b200_integrate_batch_multi",
     "ode_b200_set_work_queue", "ode_b200_com_evaluate",
     "ode_b200_tableau", "ode_b200_debug_pow", "ode_b200_debug_exp",
@@ -169,6 +170,8 @@ def load():
     lib.ode_b200_last_kernel_ms.restype = C.c_double
     lib.ode_b200_launch_count.argtypes = [C.c_void_p]
     lib.ode_b200_launch_count.restype = C.c_uint64
+    lib.ode_b200_stream.argtypes = [C.c_void_p]
+    lib.ode_b200_stream.restype = C.c_void_p
     lib.ode_b200_integrate_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(Config), C.c_int64,
                                              C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Outputs)]
     lib.ode_b200_integrate_batch.restype = C.c_int

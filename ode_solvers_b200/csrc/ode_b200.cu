@@ -280,6 +280,7 @@ extern "C" double ode_b200_last_kernel_ms(const ode_b200_ctx* c) {
     return (double)ms;
 }
 extern "C" uint64_t ode_b200_launch_count(const ode_b200_ctx* c) { return c ? c->launches : 0; }
+extern "C" void* ode_b200_stream(const ode_b200_ctx* c) { return c ? (void*)c->stream : nullptr; }
 extern "C" int ode_b200_set_work_queue(ode_b200_ctx* c, int enabled) {
     if (!c) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
     c->use_queue = enabled ? 1 : 0;
@@ -390,7 +391,7 @@ extern "C" int ode_b200_integrate_batch_device(ode_b200_ctx* c, int sys_id, cons
                                                int64_t n, const double* y0, const double* params, int per_traj,
                                                const ode_b200_outputs* out, void* cuda_stream) {
     if (!c) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+    cudaStream_t st = (cudaStream_t)cuda_stream; /* NULL = the CUDA default stream */
     return launch_device(c, sys_id, cfg, n, y0, params, per_traj, out, st);
 }
 

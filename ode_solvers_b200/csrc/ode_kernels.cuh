@@ -14,8 +14,11 @@
  *  - tableau coefficients are compile-time immediates; terms whose coefficient is a
  *    structural zero are skipped (x + k*0.0 == x for finite k). To keep the reference's
  *    behaviour when a stage derivative is inf/NaN (there inf*0.0 = NaN poisons the error
- *    estimate and the step is rejected), every stage output is tested with an integer-pipe
- *    exponent check and a hit forces err = NaN, i.e. the same reject + h/facc1 shrink;
+ *    estimate and the step is rejected), the stages whose value could otherwise vanish
+ *    behind skipped zeros (Dopri5: k2, whose a72 = e2 = d2 = 0; Dop853: k2..k5, whose b and e
+ *    weights are 0) are tested with an integer-pipe exponent check and a hit forces err = NaN,
+ *    i.e. the same reject + h/facc1 shrink. Every other stage enters the error estimate with
+ *    a non-zero weight, so a non-finite value there makes err non-finite by itself;
  *  - identical sub-expressions the source evaluates twice ((e/sc)*(e/sc), k*h) are computed
  *    once: same operands, same rounding, same bits.
  */
@@ -182,12 +185,14 @@ struct Dopri5Stepper {
                 constexpr double aij = TabDp5::a(sg, j);
                 if constexpr (aij != 0.0) {
 #pragma unroll
-                    for (int i = 0; i < N; ++i) ynext[i] = ynext[i] + (k[j][i] * h) * aij;
+                    for (int i = 0; i < N; ++i) ynext[i] = ynext[i] + (k[j][i] * h) * c_dp5_a[sg][j];
                 }
             });
-            Sys::rhs(x + h * TabDp5::c(sg), ynext, k[sg], s.p);
+            Sys::rhs(x + h * c_dp5_c[sg], ynext, k[sg], s.p);
+            if constexpr (sg == 1) { /* only k2 meets structural zeros (a72, e2, d2): see header note */
 #pragma unroll
-            for (int i = 0; i < N; ++i) bad |= nonfinite_(k[sg][i]);
+                for (int i = 0; i < N; ++i) bad |= nonfinite_(k[sg][i]);
+            }
             if constexpr (sg == 5) {
 #pragma unroll
                 for (int i = 0; i < N; ++i) ystiff[i] = ynext[i];
@@ -199,10 +204,10 @@ struct Dopri5Stepper {
         double err = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            const double ee = (((((k[0][i] * TabDp5::e(0) + k[2][i] * TabDp5::e(2)) + k[3][i] * TabDp5::e(3)) +
-                                 k[4][i] * TabDp5::e(4)) +
-                                k[5][i] * TabDp5::e(5)) +
-                               k[6][i] * TabDp5::e(6)) *
+            const double ee = (((((k[0][i] * c_dp5_e[0] + k[2][i] * c_dp5_e[2]) + k[3][i] * c_dp5_e[3]) +
+                                 k[4][i] * c_dp5_e[4]) +
+                                k[5][i] * c_dp5_e[5]) +
+                               k[6][i] * c_dp5_e[6]) *
                               h;
             const double sc = cfg.atol + fmax(fabs(s.y[i]), fabs(ynext[i])) * cfg.rtol;
             const double q = ee / sc;
@@ -238,10 +243,10 @@ struct Dopri5Stepper {
             if constexpr (DENSE || CONT) {
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
-                    rc[4][i] = (((((k[0][i] * TabDp5::d(0) + k[2][i] * TabDp5::d(2)) + k[3][i] * TabDp5::d(3)) +
-                                  k[4][i] * TabDp5::d(4)) +
-                                 k[5][i] * TabDp5::d(5)) +
-                                k[6][i] * TabDp5::d(6)) *
+                    rc[4][i] = (((((k[0][i] * c_dp5_d[0] + k[2][i] * c_dp5_d[2]) + k[3][i] * c_dp5_d[3]) +
+                                  k[4][i] * c_dp5_d[4]) +
+                                 k[5][i] * c_dp5_d[5]) +
+                                k[6][i] * c_dp5_d[6]) *
                                h;
                     const double ydiff = ynext[i] - s.y[i];
                     const double bspl = k[0][i] * h - ydiff;
@@ -425,14 +430,16 @@ struct Dop853Stepper {
                 constexpr int j = decltype(J)::value;
                 constexpr double aij = TabDp8::a(sg, j);
                 if constexpr (aij != 0.0) {
-                    const double ha = h * aij;
+                    const double ha = h * c_dp8_a[sg][j];
 #pragma unroll
                     for (int i = 0; i < N; ++i) ynext[i] = ynext[i] + k[j][i] * ha;
                 }
             });
-            Sys::rhs(x + (h * TabDp8::c(sg)), ynext, k[sg], s.p); /* c(12) = 0.0 (Q1) */
+            Sys::rhs(x + (h * c_dp8_c[sg]), ynext, k[sg], s.p); /* c(12) = 0.0 (Q1) */
+            if constexpr (sg >= 1 && sg <= 4) { /* only k2..k5 have b = e = 0: see header note */
 #pragma unroll
-            for (int i = 0; i < N; ++i) bad |= nonfinite_(k[sg][i]);
+                for (int i = 0; i < N; ++i) bad |= nonfinite_(k[sg][i]);
+            }
         });
         s.c.num_eval += 11;
         /* from here the reference's slots are: k[1] = k11 (our k[10]), k[2] = k12 (our k[11]) */
@@ -441,12 +448,12 @@ struct Dop853Stepper {
         double bsum[N], y8[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            bsum[i] = ((((((k[0][i] * TabDp8::b(0) + k[5][i] * TabDp8::b(5)) + k[6][i] * TabDp8::b(6)) +
-                          k[7][i] * TabDp8::b(7)) +
-                         k[8][i] * TabDp8::b(8)) +
-                        k[9][i] * TabDp8::b(9)) +
-                       k[10][i] * TabDp8::b(10)) +
-                      k[11][i] * TabDp8::b(11);
+            bsum[i] = ((((((k[0][i] * c_dp8_b[0] + k[5][i] * c_dp8_b[5]) + k[6][i] * c_dp8_b[6]) +
+                          k[7][i] * c_dp8_b[7]) +
+                         k[8][i] * c_dp8_b[8]) +
+                        k[9][i] * c_dp8_b[9]) +
+                       k[10][i] * c_dp8_b[10]) +
+                      k[11][i] * c_dp8_b[11];
             y8[i] = s.y[i] + bsum[i] * h;
         }
         /* error estimators and norm, dop853.rs:334-362. err_est runs over the 12 slots; slots
@@ -454,16 +461,16 @@ struct Dop853Stepper {
         double err = 0.0, err2 = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            double ee = k[0][i] * TabDp8::e(0); /* 0.0 + v == v */
-            ee = ee + k[5][i] * TabDp8::e(5);
-            ee = ee + k[6][i] * TabDp8::e(6);
-            ee = ee + k[7][i] * TabDp8::e(7);
-            ee = ee + k[8][i] * TabDp8::e(8);
-            ee = ee + k[9][i] * TabDp8::e(9);
-            ee = ee + k[10][i] * TabDp8::e(10);
-            ee = ee + k[11][i] * TabDp8::e(11);
-            const double eb = ((bsum[i] - k[0][i] * TabDp8::bhh(0)) - k[8][i] * TabDp8::bhh(1)) -
-                              k[11][i] * TabDp8::bhh(2);
+            double ee = k[0][i] * c_dp8_e[0]; /* 0.0 + v == v */
+            ee = ee + k[5][i] * c_dp8_e[5];
+            ee = ee + k[6][i] * c_dp8_e[6];
+            ee = ee + k[7][i] * c_dp8_e[7];
+            ee = ee + k[8][i] * c_dp8_e[8];
+            ee = ee + k[9][i] * c_dp8_e[9];
+            ee = ee + k[10][i] * c_dp8_e[10];
+            ee = ee + k[11][i] * c_dp8_e[11];
+            const double eb = ((bsum[i] - k[0][i] * c_dp8_bhh[0]) - k[8][i] * c_dp8_bhh[1]) -
+                              k[11][i] * c_dp8_bhh[2];
             const double sc = cfg.atol + fmax(fabs(s.y[i]), fabs(y8[i])) * cfg.rtol;
             const double q1 = ee / sc, q2 = eb / sc;
             err += q1 * q1;
@@ -516,14 +523,14 @@ struct Dop853Stepper {
                     constexpr int r = decltype(R)::value;
 #pragma unroll
                     for (int i = 0; i < N; ++i) {
-                        double v = k[0][i] * TabDp8::d(r, 0);
-                        v = v + k[5][i] * TabDp8::d(r, 5);
-                        v = v + k[6][i] * TabDp8::d(r, 6);
-                        v = v + k[7][i] * TabDp8::d(r, 7);
-                        v = v + k[8][i] * TabDp8::d(r, 8);
-                        v = v + k[9][i] * TabDp8::d(r, 9);
-                        v = v + k[10][i] * TabDp8::d(r, 10);
-                        v = v + k[11][i] * TabDp8::d(r, 11);
+                        double v = k[0][i] * c_dp8_d[r][0];
+                        v = v + k[5][i] * c_dp8_d[r][5];
+                        v = v + k[6][i] * c_dp8_d[r][6];
+                        v = v + k[7][i] * c_dp8_d[r][7];
+                        v = v + k[8][i] * c_dp8_d[r][8];
+                        v = v + k[9][i] * c_dp8_d[r][9];
+                        v = v + k[10][i] * c_dp8_d[r][10];
+                        v = v + k[11][i] * c_dp8_d[r][11];
                         rc[4 + r][i] = v;
                     }
                 });
@@ -531,45 +538,45 @@ struct Dop853Stepper {
                 double yy[N], k14[N], k15[N], k16[N];
 #pragma unroll
                 for (int i = 0; i < N; ++i)
-                    yy[i] = s.y[i] + (((((((k[0][i] * TabDp8::a(13, 0) + k[6][i] * TabDp8::a(13, 6)) +
-                                            k[7][i] * TabDp8::a(13, 7)) +
-                                           k[8][i] * TabDp8::a(13, 8)) +
-                                          k[9][i] * TabDp8::a(13, 9)) +
-                                         k[10][i] * TabDp8::a(13, 10)) +
-                                        k[11][i] * TabDp8::a(13, 11)) +
-                                       knew[i] * TabDp8::a(13, 12)) *
+                    yy[i] = s.y[i] + (((((((k[0][i] * c_dp8_a[13][0] + k[6][i] * c_dp8_a[13][6]) +
+                                            k[7][i] * c_dp8_a[13][7]) +
+                                           k[8][i] * c_dp8_a[13][8]) +
+                                          k[9][i] * c_dp8_a[13][9]) +
+                                         k[10][i] * c_dp8_a[13][10]) +
+                                        k[11][i] * c_dp8_a[13][11]) +
+                                       knew[i] * c_dp8_a[13][12]) *
                                           h;
-                Sys::rhs(x + h * TabDp8::c(13), yy, k14, s.p);
+                Sys::rhs(x + h * c_dp8_c[13], yy, k14, s.p);
 #pragma unroll
                 for (int i = 0; i < N; ++i)
-                    yy[i] = s.y[i] + (((((((k[0][i] * TabDp8::a(14, 0) + k[5][i] * TabDp8::a(14, 5)) +
-                                            k[6][i] * TabDp8::a(14, 6)) +
-                                           k[7][i] * TabDp8::a(14, 7)) +
-                                          k[10][i] * TabDp8::a(14, 10)) +
-                                         k[11][i] * TabDp8::a(14, 11)) +
-                                        knew[i] * TabDp8::a(14, 12)) +
-                                       k14[i] * TabDp8::a(14, 13)) *
+                    yy[i] = s.y[i] + (((((((k[0][i] * c_dp8_a[14][0] + k[5][i] * c_dp8_a[14][5]) +
+                                            k[6][i] * c_dp8_a[14][6]) +
+                                           k[7][i] * c_dp8_a[14][7]) +
+                                          k[10][i] * c_dp8_a[14][10]) +
+                                         k[11][i] * c_dp8_a[14][11]) +
+                                        knew[i] * c_dp8_a[14][12]) +
+                                       k14[i] * c_dp8_a[14][13]) *
                                           h;
-                Sys::rhs(x + h * TabDp8::c(14), yy, k15, s.p);
+                Sys::rhs(x + h * c_dp8_c[14], yy, k15, s.p);
 #pragma unroll
                 for (int i = 0; i < N; ++i)
-                    yy[i] = s.y[i] + (((((((k[0][i] * TabDp8::a(15, 0) + k[5][i] * TabDp8::a(15, 5)) +
-                                            k[6][i] * TabDp8::a(15, 6)) +
-                                           k[7][i] * TabDp8::a(15, 7)) +
-                                          k[8][i] * TabDp8::a(15, 8)) +
-                                         knew[i] * TabDp8::a(15, 12)) +
-                                        k14[i] * TabDp8::a(15, 13)) +
-                                       k15[i] * TabDp8::a(15, 14)) *
+                    yy[i] = s.y[i] + (((((((k[0][i] * c_dp8_a[15][0] + k[5][i] * c_dp8_a[15][5]) +
+                                            k[6][i] * c_dp8_a[15][6]) +
+                                           k[7][i] * c_dp8_a[15][7]) +
+                                          k[8][i] * c_dp8_a[15][8]) +
+                                         knew[i] * c_dp8_a[15][12]) +
+                                        k14[i] * c_dp8_a[15][13]) +
+                                       k15[i] * c_dp8_a[15][14]) *
                                           h;
-                Sys::rhs(x + h * TabDp8::c(15), yy, k16, s.p);
+                Sys::rhs(x + h * c_dp8_c[15], yy, k16, s.p);
                 s.c.num_eval += 3;
                 static_for<0, 4>([&](auto R) {
                     constexpr int r = decltype(R)::value;
 #pragma unroll
                     for (int i = 0; i < N; ++i)
-                        rc[4 + r][i] = ((((rc[4 + r][i] + knew[i] * TabDp8::d(r, 12)) + k14[i] * TabDp8::d(r, 13)) +
-                                         k15[i] * TabDp8::d(r, 14)) +
-                                        k16[i] * TabDp8::d(r, 15)) *
+                        rc[4 + r][i] = ((((rc[4 + r][i] + knew[i] * c_dp8_d[r][12]) + k14[i] * c_dp8_d[r][13]) +
+                                         k15[i] * c_dp8_d[r][14]) +
+                                        k16[i] * c_dp8_d[r][15]) *
                                        h;
                 });
             }

@@ -79,6 +79,38 @@ ODE_POW_FN ode_pow_tabs ode_pow_host_tabs(void) {
 }
 #endif
 
+/* Scalar constants of the two polynomials. On the device they are read from the constant
+ * bank (one LDCU / c[] operand) instead of being materialised as 64-bit immediates (two
+ * UMOV each), which measurably costs issue slots in the FP64-bound step loop. */
+#if defined(__CUDACC__)
+static __constant__ double c_ode_pow_k[19] = {
+    ODE_POW_LN2HI, ODE_POW_LN2LO, ODE_POW_A0, ODE_POW_A1, ODE_POW_A2, ODE_POW_A3, ODE_POW_A4, ODE_POW_A5,
+    ODE_POW_A6, ODE_EXP_INVLN2N, ODE_EXP_SHIFT, ODE_EXP_NEGLN2HIN, ODE_EXP_NEGLN2LON, ODE_EXP_C2, ODE_EXP_C3,
+    ODE_EXP_C4, ODE_EXP_C5, 0x1p1009, 0x1p-1022};
+#endif
+#if defined(__CUDA_ARCH__)
+#define ODE_K(i, lit) c_ode_pow_k[i]
+#else
+#define ODE_K(i, lit) (lit)
+#endif
+#define K_LN2HI ODE_K(0, ODE_POW_LN2HI)
+#define K_LN2LO ODE_K(1, ODE_POW_LN2LO)
+#define K_A0 ODE_K(2, ODE_POW_A0)
+#define K_A1 ODE_K(3, ODE_POW_A1)
+#define K_A2 ODE_K(4, ODE_POW_A2)
+#define K_A3 ODE_K(5, ODE_POW_A3)
+#define K_A4 ODE_K(6, ODE_POW_A4)
+#define K_A5 ODE_K(7, ODE_POW_A5)
+#define K_A6 ODE_K(8, ODE_POW_A6)
+#define K_INVLN2N ODE_K(9, ODE_EXP_INVLN2N)
+#define K_SHIFT ODE_K(10, ODE_EXP_SHIFT)
+#define K_NEGLN2HIN ODE_K(11, ODE_EXP_NEGLN2HIN)
+#define K_NEGLN2LON ODE_K(12, ODE_EXP_NEGLN2LON)
+#define K_C2 ODE_K(13, ODE_EXP_C2)
+#define K_C3 ODE_K(14, ODE_EXP_C3)
+#define K_C4 ODE_K(15, ODE_EXP_C4)
+#define K_C5 ODE_K(16, ODE_EXP_C5)
+
 #define ODE_POW_OFF 0x3fe6955500000000ULL
 #define ODE_POW_SIGN_BIAS 0x40000u /* 0x800 << 7 */
 
@@ -126,19 +158,19 @@ ODE_POW_FN double ode_exp_inline_(double x, double xtail, ode_u32 sign_bias, int
         }
         abstop = 0;
     }
-    double kd = fma(x, ODE_EXP_INVLN2N, ODE_EXP_SHIFT);
+    double kd = fma(x, K_INVLN2N, K_SHIFT);
     ode_u64 ki = ODE_ASU64(kd);
-    kd -= ODE_EXP_SHIFT;
-    double r = fma(kd, ODE_EXP_NEGLN2HIN, x);
-    r = fma(kd, ODE_EXP_NEGLN2LON, r);
+    kd -= K_SHIFT;
+    double r = fma(kd, K_NEGLN2HIN, x);
+    r = fma(kd, K_NEGLN2LON, r);
     if (has_tail) r += xtail;
     ode_u32 idx = 2u * (ode_u32)(ki & 127u);
     ode_u64 top = (ki + sign_bias) << 45;
     double tail = ODE_ASF64(T.et[idx]);
     ode_u64 sbits = T.et[idx + 1] + top;
     double r2 = r * r;
-    double p01 = fma(r, ODE_EXP_C3, ODE_EXP_C2);
-    double p23 = fma(r, ODE_EXP_C5, ODE_EXP_C4);
+    double p01 = fma(r, K_C3, K_C2);
+    double p23 = fma(r, K_C5, K_C4);
     double tmp = fma(p01, r2, tail + r);
     tmp = fma(r2 * r2, p23, tmp);
     if (abstop == 0) return ode_exp_specialcase_(tmp, sbits, ki);
@@ -225,18 +257,18 @@ ODE_POW_FN double ode_pow(double x, double y, ode_pow_tabs T) {
     double kd = (double)k;
     double invc = ODE_ASF64(T.lt[3 * i]), logc = ODE_ASF64(T.lt[3 * i + 1]), logctail = ODE_ASF64(T.lt[3 * i + 2]);
     double r = fma(z, invc, -1.0);
-    double t1 = fma(kd, ODE_POW_LN2HI, logc);
+    double t1 = fma(kd, K_LN2HI, logc);
     double t2 = t1 + r;
-    double lo1 = fma(kd, ODE_POW_LN2LO, logctail);
+    double lo1 = fma(kd, K_LN2LO, logctail);
     double lo2 = t1 - t2 + r;
-    double ar = ODE_POW_A0 * r;
+    double ar = K_A0 * r;
     double ar2 = r * ar;
     double ar3 = r * ar2;
     double hi = t2 + ar2;
     double lo3 = fma(ar, r, -ar2);
     double lo4 = t2 - hi + ar2;
-    double q = fma(ar2, fma(r, ODE_POW_A6, ODE_POW_A5), fma(r, ODE_POW_A4, ODE_POW_A3));
-    q = fma(ar2, q, fma(r, ODE_POW_A2, ODE_POW_A1));
+    double q = fma(ar2, fma(r, K_A6, K_A5), fma(r, K_A4, K_A3));
+    q = fma(ar2, q, fma(r, K_A2, K_A1));
     double lo = fma(ar3, q, lo1 + lo2 + lo3 + lo4);
     double y1 = hi + lo;
     double ltail = hi - y1 + lo;

@@ -201,6 +201,15 @@ def cx_fn_2d(name, m):
             "        return t[i][j];\n    }\n" % (name, len(m), len(m[0]), rows))
 
 
+def dev_array_1d(name, vals):
+    return "static __constant__ double %s[%d] = { %s };\n" % (name, len(vals), ", ".join(hx(v) for v in vals))
+
+
+def dev_array_2d(name, m):
+    rows = ",\n    ".join("{ " + ", ".join(hx(v) for v in r) + " }" for r in m)
+    return "static __constant__ double %s[%d][%d] = {\n    %s };\n" % (name, len(m), len(m[0]), rows)
+
+
 def main():
     a5 = square(DP5_A, 7)
     a8 = square(DP8_A_TXT, 16)
@@ -240,7 +249,18 @@ def main():
     k += "};\n\nstruct TabDp8 {\n"
     k += (cx_fn_2d("a", a8) + cx_fn_1d("b", b8) + cx_fn_1d("bhh", bhh8) + cx_fn_1d("c", c8)
           + cx_fn_2d("d", d8) + cx_fn_1d("e", e8))
-    k += "};\n\n}  // namespace ode_b200\n"
+    k += "};\n\n"
+    k += ("/* The same coefficients in the constant bank (deliberately NOT const, so the compiler cannot\n"
+          " * fold them back into immediates): an FP64 instruction reads a constant-bank operand directly\n"
+          " * (DMUL R, R, c[0x3][..]), whereas a 64-bit immediate costs two extra UMOV/IMAD.MOV per use --\n"
+          " * measured at 26% of all issued instructions before this change (profiles/r1_notes.md).\n"
+          " * The constexpr accessors above are still what `if constexpr` tests for structural zeros. */\n"
+          "#ifdef __CUDACC__\n")
+    k += dev_array_2d("c_dp5_a", a5) + dev_array_1d("c_dp5_c", DP5_C) + dev_array_1d("c_dp5_d", DP5_D)
+    k += dev_array_1d("c_dp5_e", DP5_E)
+    k += dev_array_2d("c_dp8_a", a8) + dev_array_1d("c_dp8_b", b8) + dev_array_1d("c_dp8_bhh", bhh8)
+    k += dev_array_1d("c_dp8_c", c8) + dev_array_2d("c_dp8_d", d8) + dev_array_1d("c_dp8_e", e8)
+    k += "#endif\n\n}  // namespace ode_b200\n"
     with open(os.path.join(ROOT, "ode_solvers_b200", "csrc", "ode_tableau.cuh"), "w") as f:
         f.write(k)
     print("wrote oracle/ode_tableau_c.h and ode_solvers_b200/csrc/ode_tableau.cuh")
