@@ -160,6 +160,9 @@ const char* ode_b200_system_name(int sys_id);
  */
 int ode_b200_system_from_source(const char* name, int dim, int n_params,
                                 const char* rhs_body, const char* solout_body);
+/* Compile the kernel of (sys_id, method, out_type) now instead of at the first launch; needs
+ * NVRTC but no GPU, so a source error surfaces early. No-op for built-ins. */
+int ode_b200_system_compile(int sys_id, int method, int out_type);
 
 /* ---- configuration (constructors) ----------------------------------------------- */
 /* Dopri5::new / Dop853::new defaults. method = ODE_B200_DOPRI5 | ODE_B200_DOP853. */

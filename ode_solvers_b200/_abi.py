@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libode_b200.so")
+# ODE_B200_LIB selects another build of the SAME library (kernel-tuning experiments only)
+LIB_PATH = os.environ.get("ODE_B200_LIB") or os.path.join(HERE, "libode_b200.so")
 
 # method ids / OutputType (src/dop_shared.rs:112-117) / status codes (src/dop_shared.rs:120-128)
 RK4, DOPRI5, DOP853 = 0, 1, 2
@@ -112,7 +113,7 @@ ABI_SYMBOLS = [
     "ode_b200_abi_version", "ode_b200_device_count", "ode_b200_last_error",
     "ode_b200_measure_fp64_peak",
     "ode_b200_system_builtin", "ode_b200_system_dim", "ode_b200_system_n_params",
-    "ode_b200_system_name", "ode_b200_system_from_source",
+    "ode_b200_system_name", "ode_b200_system_from_source", "ode_b200_system_compile",
     "ode_b200_config_new", "ode_b200_config_from_param", "ode_b200_config_rk4",
     "ode_b200_create", "ode_b200_destroy", "ode_b200_last_kernel_ms", "ode_b200_launch_count",
     "ode_b200_stream",
@@ -161,6 +162,8 @@ def load():
     lib.ode_b200_system_name.restype = C.c_char_p
     lib.ode_b200_system_from_source.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_char_p]
     lib.ode_b200_system_from_source.restype = C.c_int
+    lib.ode_b200_system_compile.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.ode_b200_system_compile.restype = C.c_int
     declare_config_fns(lib, "ode_b200_")
     lib.ode_b200_create.argtypes = [C.c_int]
     lib.ode_b200_create.restype = C.c_void_p

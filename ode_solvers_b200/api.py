@@ -174,6 +174,10 @@ class System:
             raise Ode200Error(_abi.last_error())
         return cls(sid, params)
 
+    def compile(self, method, out_type=_abi.OUT_SPARSE):
+        """NVRTC-compile this system's kernel for (method, out_type) now (no GPU needed)."""
+        _check(_abi.load().ode_b200_system_compile(self.sys_id, int(method), int(out_type)), "system_compile")
+
     def with_params(self, params):
         return System(self.sys_id, params)
 

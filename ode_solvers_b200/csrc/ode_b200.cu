@@ -110,6 +110,18 @@ extern "C" int ode_b200_system_from_source(const char* name, int dim, int n_para
     return kNumBuiltins + id;
 }
 
+extern "C" int ode_b200_system_compile(int sys_id, int method, int out_type) {
+    SysInfo s;
+    if (!sys_info(sys_id, &s)) return fail(ODE_B200_ERR_UNKNOWN_SYSTEM, "bad sys_id");
+    if (method < ODE_B200_RK4 || method > ODE_B200_DOP853 || out_type < ODE_B200_OUT_DENSE ||
+        out_type > ODE_B200_OUT_CONTINUOUS)
+        return fail(ODE_B200_ERR_INVALID_ARGUMENT, "system_compile: bad method / out_type");
+    if (!s.jit) return ODE_B200_SUCCESS; /* built-ins are compiled ahead of time */
+    std::string err;
+    if (!jit_compile(sys_id - kNumBuiltins, method, out_type, &err)) return fail(ODE_B200_ERR_COMPILE, err);
+    return ODE_B200_SUCCESS;
+}
+
 /* ------------------------------------------------------------------ constructors */
 static const double kEps = 2.220446049250313e-16; /* f64::EPSILON */
 

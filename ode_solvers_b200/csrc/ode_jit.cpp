@@ -28,7 +28,8 @@ namespace ode_b200 {
 namespace {
 
 struct Api {
-    bool ok = false;
+    bool ok = false;     /* NVRTC usable (compiling needs no GPU) */
+    bool drv_ok = false; /* driver API usable (loading / launching) */
     std::string why;
     /* nvrtc */
     nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*,
@@ -66,11 +67,6 @@ Api& api() {
             a.why = "cannot load libnvrtc.so.12";
             return;
         }
-        void* drv = open_first({"libcuda.so.1", "libcuda.so"});
-        if (!drv) {
-            a.why = "cannot load libcuda.so.1 (no NVIDIA driver)";
-            return;
-        }
 #define L(h, field, sym)                                         \
     a.field = (decltype(a.field))dlsym(h, sym);                  \
     if (!a.field) {                                              \
@@ -87,13 +83,19 @@ Api& api() {
         L(rtc, AddNameExpression, "nvrtcAddNameExpression")
         L(rtc, GetLoweredName, "nvrtcGetLoweredName")
         L(rtc, GetErrorString, "nvrtcGetErrorString")
+        a.ok = true;
+        void* drv = open_first({"libcuda.so.1", "libcuda.so"});
+        if (!drv) {
+            a.why = "cannot load libcuda.so.1 (no NVIDIA driver)";
+            return;
+        }
         L(drv, ModuleLoadData, "cuModuleLoadData")
         L(drv, ModuleGetFunction, "cuModuleGetFunction")
         L(drv, LaunchKernel, "cuLaunchKernel")
         L(drv, Occupancy, "cuOccupancyMaxActiveBlocksPerMultiprocessor")
         L(drv, GetErrorName, "cuGetErrorName")
 #undef L
-        a.ok = true;
+        a.drv_ok = true;
     });
     return a;
 }
@@ -126,11 +128,19 @@ std::string make_source(const JitSystem& s, const std::string& stepper) {
            "\n  }\n";
     src += "  ODE_DEV static bool solout(double x, const double* y, const double* dy, const double* p) {\n" +
            (s.has_solout ? s.solout_body : std::string("return false;")) + "\n  }\n};\n}\n";
-    src += "template __global__ void ode_b200::ode_step_loop_kernel<" + stepper + " >(const ode_b200::KernelArgs);\n";
+    src += "template __global__ void ode_b200::ode_step_loop_kernel<" + stepper +
+           " >(const __grid_constant__ ode_b200::KernelArgs);\n";
     return src;
 }
 
-bool compile(const JitSystem& s, int method, int out_type, Compiled* out, std::string* err) {
+struct Cubin {
+    std::vector<char> bin;
+    std::string mangled;
+};
+/* (system, method, out_type) -> cubin; device independent */
+std::map<std::tuple<int, int, int>, Cubin> g_cubins;
+
+bool compile_cubin(const JitSystem& s, int method, int out_type, Cubin* out, std::string* err) {
     Api& a = api();
     const std::string stepper = stepper_expr(method, out_type);
     const std::string src = make_source(s, stepper);
@@ -162,18 +172,39 @@ bool compile(const JitSystem& s, int method, int out_type, Compiled* out, std::s
         a.DestroyProgram(&prog);
         return false;
     }
-    const std::string mangled = lowered;
+    out->mangled = lowered;
     size_t nbin = 0;
     a.GetCUBINSize(prog, &nbin);
-    std::vector<char> bin(nbin);
-    r = a.GetCUBIN(prog, bin.data());
+    out->bin.resize(nbin);
+    r = a.GetCUBIN(prog, out->bin.data());
     a.DestroyProgram(&prog);
     if (r != NVRTC_SUCCESS || nbin == 0) {
         *err = "nvrtcGetCUBIN failed";
         return false;
     }
-    CUresult cr = a.ModuleLoadData(&out->mod, bin.data());
-    if (cr == CUDA_SUCCESS) cr = a.ModuleGetFunction(&out->fn, out->mod, mangled.c_str());
+    return true;
+}
+
+/* g_mu held */
+const Cubin* get_cubin(int idx, const JitSystem& s, int method, int out_type, std::string* err) {
+    const int o = method == ODE_B200_RK4 ? 0 : (method == ODE_B200_DOP853 && out_type != ODE_B200_OUT_DENSE
+                                                    ? ODE_B200_OUT_SPARSE : out_type);
+    auto key = std::make_tuple(idx, method, o);
+    auto it = g_cubins.find(key);
+    if (it != g_cubins.end()) return &it->second;
+    Cubin c;
+    if (!compile_cubin(s, method, out_type, &c, err)) return nullptr;
+    return &(g_cubins[key] = std::move(c));
+}
+
+bool load(const Cubin& cb, Compiled* out, std::string* err) {
+    Api& a = api();
+    if (!a.drv_ok) {
+        *err = "JIT launch unavailable: " + a.why;
+        return false;
+    }
+    CUresult cr = a.ModuleLoadData(&out->mod, cb.bin.data());
+    if (cr == CUDA_SUCCESS) cr = a.ModuleGetFunction(&out->fn, out->mod, cb.mangled.c_str());
     if (cr != CUDA_SUCCESS) {
         const char* nm = "?";
         a.GetErrorName(cr, &nm);
@@ -198,6 +229,21 @@ int jit_register(const char* name, int dim, int n_params, const char* rhs_body, 
     if (s->has_solout) s->solout_body = solout_body;
     g_systems.push_back(std::move(s));
     return (int)g_systems.size() - 1;
+}
+
+bool jit_compile(int idx, int method, int out_type, std::string* err) {
+    Api& a = api();
+    if (!a.ok) {
+        *err = "JIT unavailable: " + a.why;
+        return false;
+    }
+    const JitSystem* s = jit_system(idx);
+    if (!s) {
+        *err = "bad JIT system index";
+        return false;
+    }
+    std::lock_guard<std::mutex> g(g_mu);
+    return get_cubin(idx, *s, method, out_type, err) != nullptr;
 }
 
 const JitSystem* jit_system(int idx) {
@@ -227,7 +273,8 @@ bool jit_launch(int idx, int device, int num_sms, int method, int out_type, cons
         auto key = std::make_tuple(idx, device, method, o);
         auto it = g_cache.find(key);
         if (it == g_cache.end()) {
-            if (!compile(*s, method, out_type, &c, err)) return false;
+            const Cubin* cb = get_cubin(idx, *s, method, out_type, err);
+            if (!cb || !load(*cb, &c, err)) return false;
             if (a.Occupancy(&c.per_sm, c.fn, block, 0) != CUDA_SUCCESS || c.per_sm < 1) {
                 *err = "JIT kernel does not fit on an SM";
                 return false;

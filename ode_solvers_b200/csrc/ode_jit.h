@@ -23,6 +23,9 @@ int jit_register(const char* name, int dim, int n_params, const char* rhs_body, 
                  std::string* err);
 const JitSystem* jit_system(int idx);
 
+/* NVRTC-compile one (method, out_type) kernel of a registered system to a cubin (no GPU needed) */
+bool jit_compile(int idx, int method, int out_type, std::string* err);
+
 /* compile (once per system/device/method/out_type), size the grid and launch on `stream` */
 bool jit_launch(int idx, int device, int num_sms, int method, int out_type, const void* kernel_args,
                 size_t kernel_args_bytes, int block, long long blocks_all, int use_queue, void* stream,

@@ -654,8 +654,23 @@ struct Dop853Stepper {
 };
 
 /* ============================================================================ kernels */
+/*
+ * Resident CTAs per SM the register allocator must leave room for. The step loop is bound by
+ * dependent FP64 latency (ncu: "wait" is the top stall), so warps per scheduler matter more
+ * than a few spilled scalars: 5 CTAs x 4 warps (<= 96 registers) measured 31.4 ms against
+ * 46.4 ms at 255 registers and 32.7 ms at 126 for the 2^20-trajectory Lorenz/Dopri5 run, and
+ * 70.8 ms against 96.1 ms for Kepler/Dop853 (profiles/r1_notes.md).
+ */
+#ifdef ODE_B200_MIN_BLOCKS
+template <int N>
+constexpr int min_blocks_for_dim() { return ODE_B200_MIN_BLOCKS; }
+#else
+template <int N>
+constexpr int min_blocks_for_dim() { return N <= 8 ? 5 : 2; }
+#endif
+
 template <class Stepper>
-__global__ void __launch_bounds__(kBlockThreads) ode_step_loop_kernel(const __grid_constant__ KernelArgs a) {
+__global__ void __launch_bounds__(kBlockThreads, min_blocks_for_dim<Stepper::N>()) ode_step_loop_kernel(const __grid_constant__ KernelArgs a) {
     run_lanes_<Stepper>(a);
 }
 

@@ -1,0 +1,220 @@
+"""The crate-shaped host API (ode_solvers_b200.api) on the GPU, written like the reference's
+own tests (src/rk4.rs:223-306, src/dopri5.rs:545-581, src/dop853.rs:609-620,
+src/continuous_output_model.rs:121-252, tests/dopri5.rs) plus the batched extras: NVRTC-registered
+user systems, device ContinuousOutputModel::evaluate, error statuses, the multi-GPU entry."""
+import math
+
+import numpy as np
+import pytest
+
+import ode_solvers_b200 as ob
+import oracle
+from ode_solvers_b200 import workloads as W
+from parity_util import assert_same_outputs, same_f64
+
+pytestmark = pytest.mark.gpu
+
+
+def analytic(t):
+    return -math.log(t ** 3 + 1.0)
+
+
+# ---- src/rk4.rs tests
+def test_rk4_test1_to_test4():
+    s = ob.Rk4.new(ob.System.builtin("test_rk4_1"), 0.0, [1.0], 0.2, 0.1)
+    s.integrate()
+    assert abs(s.x_out()[-1] - 0.2) < 1e-8
+    assert abs(s.y_out()[1][0] - 0.95369) < 1e-5 and abs(s.y_out()[2][0] - 0.91451) < 1e-5
+    s = ob.Rk4.new(ob.System.builtin("test_rk4_2"), 0.0, [-1.0], 0.5, 0.1)
+    s.integrate()
+    assert abs(s.x_out()[-1] - 0.5) < 1e-8
+    assert abs(s.y_out()[3][0] + 0.82246) < 1e-5 and abs(s.y_out()[5][0] + 0.81959) < 1e-5
+    s = ob.Rk4.new(ob.System.builtin("test_exp"), 0.0, [1.0], 1.0, 0.1)
+    st = s.integrate()
+    out = s.y_out()
+    assert abs(out[5][0] - 0.913059839) < 1e-9 and abs(out[8][0] - 0.9838057659) < 1e-9
+    assert abs(out[10][0] - 1.0715783953) < 1e-9 and len(out) == 11
+    assert (st.num_eval, st.accepted_steps, st.rejected_steps) == (40, 10, 0)
+    s = ob.Rk4.new(ob.System.builtin("test_exp_stop", [0.5]), 0.0, [1.0], 1.0, 0.1)
+    s.integrate()
+    assert abs(s.x_out()[-1] - 0.5) < 1e-9 and abs(s.y_out()[5][0] - 0.913059839) < 1e-9 and len(s.y_out()) == 6
+
+
+# ---- src/dopri5.rs tests
+def test_dopri5_test1_and_continuous_panic():
+    s = ob.Dopri5.new(ob.System.builtin("test_exp_stop", [0.5]), 0.0, 1.0, 0.1, [1.0], 1e-12, 1e-6)
+    s.integrate()
+    assert abs(s.x_out()[-1] - 0.5) < 1e-9
+    assert abs(s.y_out()[5][0] - 0.9130611474392001) < 1e-9
+    assert s.y_out()[5][0] == 0.9130611474392001
+    s = ob.Dopri5.from_param(ob.System.builtin("test_exp_stop", [0.5]), 0.0, 1.0, 0.1, [1.0], 1e-12, 1e-6, 0.1, 0.2,
+                             0.3, 2.0, 5.0, 0.1, 10000, 1000, ob.OutputType.Continuous)
+    with pytest.raises(RuntimeError):  # #[should_panic], dopri5.rs:558-581
+        s.integrate()
+
+
+# ---- src/dop853.rs test
+def test_dop853_test1():
+    s = ob.Dop853.new(ob.System.builtin("test_exp_stop", [0.5]), 0.0, 1.0, 0.1, [1.0], 1e-12, 1e-6)
+    s.integrate()
+    assert abs(s.x_out()[-1] - 0.5) < 1e-9
+    assert abs(s.y_out()[5][0] - 0.912968195) < 1e-9
+
+
+# ---- tests/dopri5.rs
+def test_integration_dense():
+    s = ob.Dopri5.new(ob.System.builtin("test_cubic"), 0.0, 6.0, 0.1, [0.0], 1e-10, 1e-10)
+    s.integrate()
+    ts, ys = s.results().get()
+    assert len(ts) == 61 and len(ys) == 61
+    for t, y in zip(ts, ys):
+        assert abs(y[0] - analytic(t)) < 1e-8
+
+
+def test_integration_continuous_output_model():
+    s = ob.Dopri5.new(ob.System.builtin("test_cubic"), 0.0, 6.0, 0.1, [0.0], 1e-10, 1e-10)
+    com = ob.ContinuousOutputModel.default()
+    s.integrate_with_continuous_output_model(com)
+    assert com.evaluate(-0.0001) is None and com.evaluate(0.0) is not None
+    assert com.evaluate(6.0) is not None and com.evaluate(6.0001) is None
+    for i in range(100):
+        t = i * (6.0 / 100)
+        assert abs(com.evaluate(t)[0] - analytic(t)) < 1e-9
+    # serde-shaped round trip keeps every bit
+    back = ob.ContinuousOutputModel.from_dict(com.to_dict())
+    assert back.evaluate(3.21)[0] == com.evaluate(3.21)[0]
+
+
+def test_integration_continuous_output_model_and_stopping_condition():
+    s = ob.Dopri5.new(ob.System.builtin("test_cubic_stop", [4.1]), 0.0, 6.0, 0.1, [0.0], 1e-10, 1e-10)
+    com = ob.ContinuousOutputModel.default()
+    s.integrate_with_continuous_output_model(com)
+    assert com.evaluate(-0.0001) is None and com.evaluate(0.0) is not None
+    assert com.evaluate(4.1) is not None and com.evaluate(4.1 + 0.1) is None
+    assert 4.1 <= com.bounds()[1] < 4.2
+    for i in range(100):
+        t = i * ((6.0 - 4.1) / 100)
+        assert abs(com.evaluate(t)[0] - analytic(t)) < 1e-9
+
+
+# ---- src/continuous_output_model.rs tests, evaluated by the device kernel
+def test_com_unit_tests_on_device():
+    m = ob.ContinuousOutputModel.default()
+    m.add_interval(2.0, [[0.2], [1.0], [-2.5]], 0.1)
+    m.add_interval(5.0, [[-1.5], [0.4], [1.2]], 0.2)
+    assert m.evaluate(-0.1) is None and m.evaluate(5.1) is None
+    for x, want in ((0.0, 0.2), (1.2, 342.2), (2.0, 970.2), (2.5, -5.0), (5.0, -247.5)):
+        assert abs(m.evaluate(x)[0] - want) < 1e-9 * max(1.0, abs(want))
+    m = ob.ContinuousOutputModel.default()
+    m.add_interval(2.0, [[0.2], [1.0], [-2.5], [0.3]], 0.1)
+    m.add_interval(5.0, [[-1.5], [0.4], [1.2], [2.7]], 0.2)
+    for x, want in ((0.0, 0.2), (1.2, -133.0), (2.0, -1309.8), (2.5, -30.3125), (5.0, -8752.5)):
+        assert abs(m.evaluate(x)[0] - want) < 1e-9 * max(1.0, abs(want))
+    assert ob.ContinuousOutputModel.default().evaluate(0.0) is None
+
+
+def test_batched_com_evaluate_matches_oracle_bitwise():
+    n = 200
+    y0, p = W.lorenz_ensemble(n, offset=3)
+    cfg = ob.config_new(ob.DOPRI5, 0.0, 3.0, 0.1, 1e-6, 1e-6, out_type=ob.OUT_CONTINUOUS)
+    g = ob.integrate_batch(ob.System.builtin("lorenz"), cfg, y0, p, out_cap=400, com_cap=400)
+    assert (g.com_count <= 400).all()
+    xq = np.linspace(-0.5, 3.5, 97)
+    y, found = ob.com_evaluate_batch(g, xq)
+    for i in range(0, n, 7):
+        for q, x in enumerate(xq):
+            r = oracle.com_evaluate(g, i, x)
+            assert (r is not None) == bool(found[i, q])
+            if r is not None:
+                assert same_f64(y[i, q], r).all()
+
+
+# ---- user systems through NVRTC (the `System` trait implemented by the user)
+def test_user_system_from_source_matches_builtin_bitwise():
+    f = ob.System.from_source(
+        "user_lorenz", 3, 3,
+        "dy[0] = p[0] * (y[1] - y[0]);\n dy[1] = y[0] * (p[2] - y[2]) - y[1];\n dy[2] = y[0] * y[1] - p[1] * y[2];")
+    y0, p = W.lorenz_ensemble(300, offset=11)
+    for cfg in (ob.config_new(ob.DOPRI5, 0.0, 4.0, 0.1, 1e-6, 1e-6, out_type=ob.OUT_SPARSE),
+                ob.config_new(ob.DOP853, 0.0, 4.0, 0.1, 1e-6, 1e-6, out_type=ob.OUT_SPARSE),
+                ob.config_new(ob.DOPRI5, 0.0, 4.0, 0.1, 1e-6, 1e-6), ob.config_rk4(0.0, 1.0, 1e-3)):
+        cap = 60 if cfg.out_type == ob.OUT_DENSE and cfg.method != ob.RK4 else 0
+        a = ob.integrate_batch(f, cfg, y0, p, out_cap=cap)
+        b = ob.integrate_batch(ob.System.builtin("lorenz"), cfg, y0, p, out_cap=cap)
+        assert_same_outputs(a, b, "jit vs builtin m%d" % cfg.method)
+
+
+def test_user_system_with_solout_and_exp():
+    f = ob.System.from_source("user_exp_stop", 1, 1, "dy[0] = (5.0 * x * x - y[0]) / exp_d(x + y[0]);",
+                              "return x >= p[0];")
+    s = ob.Dopri5.new(f.with_params([0.5]), 0.0, 1.0, 0.1, [1.0], 1e-12, 1e-6)
+    s.integrate()
+    assert s.y_out()[5][0] == 0.9130611474392001 and abs(s.x_out()[-1] - 0.5) < 1e-9
+
+
+def test_user_system_compile_error_is_reported():
+    f = ob.System.from_source("broken", 1, 0, "dy[0] = undefined_symbol;")
+    with pytest.raises(ob.Ode200Error) as e:
+        ob.integrate_batch(f, ob.config_rk4(0.0, 1.0, 0.1), np.ones((1, 4)))
+    assert "undefined_symbol" in str(e.value)
+
+
+# ---- IntegrationError variants
+def test_integration_errors():
+    lor = ob.System.builtin("lorenz", W.LORENZ_PARAMS)
+    s = ob.Dopri5.from_param(lor, 0.0, 20.0, 0.1, [1.0, 1.0, 1.0], 1e-6, 1e-6, 0.9, 0.04, 0.2, 10.0, 20.0, 0.0, 50,
+                             1000, ob.OutputType.Sparse)
+    with pytest.raises(ob.MaxNumStepReached) as e:
+        s.integrate()
+    assert e.value.n_step == 51 and len(s.x_out()) > 1  # partial results stay readable
+    rob = ob.System.builtin("robertson", W.ROBERTSON_K)
+    s = ob.Dopri5.from_param(rob, 0.0, 40.0, 1.0, [1.0, 0.0, 0.0], 1e-6, 1e-8, 0.9, 0.04, 0.2, 10.0, 40.0, 0.0,
+                             100000, 10, ob.OutputType.Sparse)
+    with pytest.raises(ob.StiffnessDetected):
+        s.integrate()
+    s = ob.Dopri5.from_param(rob, 0.0, 40.0, 1.0, [1.0, 0.0, 0.0], 1e-6, 1e-8, 0.9, 0.04, 0.2, 10.0, 40.0, 0.0,
+                             100000, 0, ob.OutputType.Sparse)
+    with pytest.raises(ob.UnsupportedDomain):
+        s.integrate()
+
+
+def test_error_and_nonfinite_paths_match_oracle_bitwise():
+    """blow-up ODE y' = y^2 style behaviour via Robertson with huge rate constants and tight n_max:
+    rejected-step shrinking, underflow and max-step exits must agree bit for bit."""
+    n = 256
+    y0, k = W.robertson_sweep(n, offset=77)
+    k = k * np.array([[1.0], [1e6], [1e8]])
+    for method in (ob.DOPRI5, ob.DOP853):
+        cfg = ob.config_from_param(method, 0.0, 1e6, 1.0, 1e-9, 1e-12, 0.9, 0.04 if method == ob.DOPRI5 else 0.0, 0.2,
+                                   10.0, 1e6, 0.0, 3000, 20, ob.OUT_SPARSE)
+        g = ob.integrate_batch(ob.System.builtin("robertson"), cfg, y0, k)
+        o = oracle.integrate_batch("robertson", cfg, y0, k)
+        assert_same_outputs(g, o, "robertson stiff m%d" % method)
+        assert (g.status != ob.OK).any()
+    # non-finite initial state: every attempt is rejected until the step size underflows
+    y0 = np.array([[np.inf, np.nan, 1e308, 1.0]] * 3)
+    cfg = ob.config_new(ob.DOPRI5, 0.0, 1.0, 0.1, 1e-6, 1e-6, out_type=ob.OUT_SPARSE)
+    g = ob.integrate_batch(ob.System.builtin("lorenz"), cfg, y0, W.LORENZ_PARAMS)
+    o = oracle.integrate_batch("lorenz", cfg, y0, W.LORENZ_PARAMS)
+    assert_same_outputs(g, o, "non-finite y0")
+
+
+def test_multi_gpu_entry_with_one_gpu_matches_single():
+    y0, p = W.kepler_sweep(777, offset=9)
+    cfg = ob.config_new(ob.DOP853, 0.0, W.kepler_period(), 60.0, 1e-10, 1e-10, out_type=ob.OUT_SPARSE)
+    f = ob.System.builtin("kepler")
+    a = ob.integrate_batch(f, cfg, y0, p)
+    lib = ob._abi.load()
+    import ctypes as C
+    out = ob._abi.HostOutputs(777, 6)
+    s = out.struct()
+    rc = lib.ode_b200_integrate_batch_multi(f.sys_id, C.byref(cfg), 777, y0.ctypes.data, p.ctypes.data, 0, 1,
+                                            C.byref(s))
+    assert rc == 0
+    assert_same_outputs(a, out, "multi(1) vs single")
+    if ob.device_count() >= 2:
+        out2 = ob._abi.HostOutputs(777, 6)
+        s2 = out2.struct()
+        assert lib.ode_b200_integrate_batch_multi(f.sys_id, C.byref(cfg), 777, y0.ctypes.data, p.ctypes.data, 0, 2,
+                                                  C.byref(s2)) == 0
+        assert_same_outputs(a, out2, "multi(2) vs single")

@@ -1,0 +1,240 @@
+"""Pin the CPU oracle against EVERY golden value / known-answer test the reference's own
+tests hold for the hot path. The Rust crate cannot be built in
+this image, so these vectors (asserted by the crate's tests to 1e-9 / 1e-5 / 1e-8) are what
+anchors the oracle; beyond those tolerances bit-level parity with the crate is unpinned.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import oracle
+from ode_solvers_b200 import _abi as A
+
+
+def _one(system, cfg, y0, params=None, cap=256, com_cap=0):
+    return oracle.integrate_batch(system, cfg, np.asarray(y0, dtype=float).reshape(-1, 1), params, out_cap=cap,
+                                  com_cap=com_cap)
+
+
+# ---------------------------------------------------------------- src/rk4.rs:223-306
+def test_rk4_test1():  # rk4.rs:223-233 (and DVector twin :272-282)
+    o = _one("test_rk4_1", oracle.config_rk4(0.0, 0.2, 0.1), [1.0])
+    assert abs(o.out_x[0, o.out_count[0] - 1] - 0.2) < 1e-8
+    assert abs(o.out_y[0, 1, 0] - 0.95369) < 1e-5
+    assert abs(o.out_y[0, 2, 0] - 0.91451) < 1e-5
+
+
+def test_rk4_test2():  # rk4.rs:235-245
+    o = _one("test_rk4_2", oracle.config_rk4(0.0, 0.5, 0.1), [-1.0])
+    assert abs(o.out_x[0, o.out_count[0] - 1] - 0.5) < 1e-8
+    assert abs(o.out_y[0, 3, 0] + 0.82246) < 1e-5
+    assert abs(o.out_y[0, 5, 0] + 0.81959) < 1e-5
+
+
+def test_rk4_test3():  # rk4.rs:247-257
+    o = _one("test_exp", oracle.config_rk4(0.0, 1.0, 0.1), [1.0])
+    assert abs(o.out_y[0, 5, 0] - 0.913059839) < 1e-9
+    assert abs(o.out_y[0, 8, 0] - 0.9838057659) < 1e-9
+    assert abs(o.out_y[0, 10, 0] - 1.0715783953) < 1e-9
+    assert o.out_count[0] == 11
+
+
+def test_rk4_test4_solout():  # rk4.rs:259-270
+    o = _one("test_exp_stop", oracle.config_rk4(0.0, 1.0, 0.1), [1.0], [0.5])
+    assert abs(o.out_x[0, o.out_count[0] - 1] - 0.5) < 1e-9
+    assert abs(o.out_y[0, 5, 0] - 0.913059839) < 1e-9
+    assert o.out_count[0] == 6
+
+
+# ---------------------------------------------------------------- src/dopri5.rs:545-556
+def test_dopri5_test1_golden():
+    o = _one("test_exp_stop", oracle.config_new(A.DOPRI5, 0.0, 1.0, 0.1, 1e-12, 1e-6), [1.0], [0.5])
+    assert abs(o.out_x[0, o.out_count[0] - 1] - 0.5) < 1e-9
+    assert abs(o.out_y[0, 5, 0] - 0.9130611474392001) < 1e-9
+    # the survey's restatement reproduced the crate's printed value to the last digit
+    assert o.out_y[0, 5, 0] == 0.9130611474392001
+
+
+# ---------------------------------------------------------------- src/dop853.rs:609-620
+def test_dop853_test1_golden():
+    o = _one("test_exp_stop", oracle.config_new(A.DOP853, 0.0, 1.0, 0.1, 1e-12, 1e-6), [1.0], [0.5])
+    assert abs(o.out_x[0, o.out_count[0] - 1] - 0.5) < 1e-9
+    assert abs(o.out_y[0, 5, 0] - 0.912968195) < 1e-9  # only reachable with the c12 = 0 quirk (Q1)
+    assert o.accepted[0] == 103
+
+
+# ---------------------------------------------------------------- tests/dopri5.rs
+def _analytic(t):
+    return -math.log(t ** 3 + 1.0)
+
+
+def test_integration_dense_61_samples():  # tests/dopri5.rs:33-61
+    o = _one("test_cubic", oracle.config_new(A.DOPRI5, 0.0, 6.0, 0.1, 1e-10, 1e-10), [0.0])
+    assert o.out_count[0] == 61
+    for s in range(61):
+        assert abs(o.out_y[0, s, 0] - _analytic(o.out_x[0, s])) < 1e-8
+
+
+def test_integration_continuous_output_model():  # tests/dopri5.rs:63-95
+    cfg = oracle.config_new(A.DOPRI5, 0.0, 6.0, 0.1, 1e-10, 1e-10, out_type=A.OUT_CONTINUOUS)
+    o = _one("test_cubic", cfg, [0.0], cap=2048, com_cap=2048)
+    assert o.com_count[0] == o.accepted[0]
+    assert oracle.com_evaluate(o, 0, -0.0001) is None
+    assert oracle.com_evaluate(o, 0, 0.0) is not None
+    assert oracle.com_evaluate(o, 0, 6.0) is not None
+    assert oracle.com_evaluate(o, 0, 6.0001) is None
+    for i in range(100):
+        t = i * (6.0 / 100)
+        assert abs(oracle.com_evaluate(o, 0, t)[0] - _analytic(t)) < 1e-9
+
+
+def test_integration_continuous_output_model_with_stop():  # tests/dopri5.rs:97-131
+    cfg = oracle.config_new(A.DOPRI5, 0.0, 6.0, 0.1, 1e-10, 1e-10, out_type=A.OUT_CONTINUOUS)
+    o = _one("test_cubic_stop", cfg, [0.0], [4.1], cap=2048, com_cap=2048)
+    assert oracle.com_evaluate(o, 0, -0.0001) is None
+    assert oracle.com_evaluate(o, 0, 0.0) is not None
+    assert oracle.com_evaluate(o, 0, 4.1) is not None
+    assert oracle.com_evaluate(o, 0, 4.2) is None
+    upper = o.com_break[0, o.com_count[0] - 1]
+    assert 4.1 <= upper < 4.2
+    assert upper == 4.154050403158099  # survey fixture
+    for i in range(100):
+        t = i * ((6.0 - 4.1) / 100)
+        assert abs(oracle.com_evaluate(o, 0, t)[0] - _analytic(t)) < 1e-9
+
+
+# ---------------------------------------------------------------- src/continuous_output_model.rs:121-252
+def _com(intervals, lower=0.0):
+    m = len(intervals[0][1])
+    out = A.HostOutputs(1, 1, 0, len(intervals), max(m, 1))
+    out.com_lower[0] = lower
+    for q, (bp, coef, step) in enumerate(intervals):
+        out.com_break[0, q] = bp
+        out.com_step[0, q] = step
+        for r, c in enumerate(coef):
+            out.com_coef[0, q, r, 0] = c
+    out.com_count[0] = len(intervals)
+    out.m = m
+    out.com_coef = np.ascontiguousarray(out.com_coef[:, :, :max(m, 1)])
+    return out
+
+
+def _ev(out, x):
+    r = oracle.com_evaluate(out, 0, x)
+    return None if r is None else r[0]
+
+
+def test_com_odd_number_of_coefficients():  # continuous_output_model.rs:121-170
+    o = _com([(2.0, [0.2, 1.0, -2.5], 0.1), (5.0, [-1.5, 0.4, 1.2], 0.2)])
+    assert _ev(o, -0.1) is None and _ev(o, 5.1) is None
+    for x, want in ((0.0, 0.2), (1.2, 342.2), (2.0, 970.2), (2.5, -5.0), (5.0, -247.5)):
+        assert abs(_ev(o, x) - want) < 1e-9 * max(1.0, abs(want))
+
+
+def test_com_even_number_of_coefficients():  # continuous_output_model.rs:172-228
+    o = _com([(2.0, [0.2, 1.0, -2.5, 0.3], 0.1), (5.0, [-1.5, 0.4, 1.2, 2.7], 0.2)])
+    for x, want in ((0.0, 0.2), (1.2, -133.0), (2.0, -1309.8), (2.5, -30.3125), (5.0, -8752.5)):
+        assert abs(_ev(o, x) - want) < 1e-9 * max(1.0, abs(want))
+
+
+def test_com_empty_model():  # continuous_output_model.rs:230-236
+    out = A.HostOutputs(1, 1, 0, 1, 1)
+    out.com_count[0] = 0
+    assert _ev(out, 0.0) is None and _ev(out, 3.0) is None
+
+
+def test_com_interval_index_boundaries():  # continuous_output_model.rs:238-252 (via evaluate: Some/None)
+    o = _com([(2.0, [1.0], 0.1), (5.0, [2.0], 0.1)])
+    assert _ev(o, -0.001) is None
+    for x, want in ((0.0, 1.0), (1.3, 1.0), (2.0, 1.0), (3.2, 2.0), (5.0, 2.0)):
+        assert _ev(o, x) == want
+    assert _ev(o, 5.0001) is None
+
+
+# ---------------------------------------------------------------- SURVEY.md section 6 fixtures
+LOR = [10.0, 8.0 / 3.0, 28.0]
+
+
+@pytest.mark.parametrize("method,tol,x_end,out_type,dx,want", [
+    (A.DOPRI5, 1e-6, 20.0, A.OUT_SPARSE, 0.1, (4767, 766, 28, 767,
+                                               (14.552660452644837, 15.49621280803895, 34.21258074295054))),
+    (A.DOP853, 1e-6, 20.0, A.OUT_SPARSE, 0.1, (3955, 256, 80, 257,
+                                               (14.342534819828142, 14.376276669180545, 34.827579579514776))),
+    (A.DOP853, 1e-4, 100.0, A.OUT_DENSE, 1e-3, (15787, 855, 269, 100001,
+                                                (11.050144919666055, 16.885442582557765, 21.887923123488036))),
+    (A.DOPRI5, 1e-6, 100.0, A.OUT_DENSE, 1e-3, (27159, 4337, 189, 100001,
+                                                (14.973997501020634, 16.725467241968342, 34.01245566005732))),
+])
+def test_lorenz_fixtures(method, tol, x_end, out_type, dx, want):
+    """examples/lorenz.rs:18-27 (literal Dop853 1e-4 run) and BASELINE config 1 (Dopri5 1e-6)."""
+    cfg = oracle.config_new(method, 0.0, x_end, dx, tol, tol, out_type=out_type)
+    o = _one("lorenz", cfg, [1.0, 1.0, 1.0], LOR, cap=0)
+    assert (o.num_eval[0], o.accepted[0], o.rejected[0], o.out_count[0]) == want[:4]
+    assert tuple(o.y_final[:, 0]) == want[4]
+    assert o.status[0] == A.OK
+
+
+def test_lorenz_rk4_fixture():
+    o = _one("lorenz", oracle.config_rk4(0.0, 20.0, 1e-3), [1.0, 1.0, 1.0], LOR, cap=0)
+    assert (o.num_eval[0], o.accepted[0], o.out_count[0]) == (80000, 20000, 20001)
+    assert o.x_final[0] == 20.00000000000146  # x accumulates x += h, no clamp (Q10)
+    assert tuple(o.y_final[:, 0]) == (13.7932290895289, 12.951847113228158, 34.901636990552234)
+
+
+def test_kepler_example_fixture():
+    """examples/kepler_orbit.rs:20-36 literal: Dopri5 1e-10, dx = 60, 5 periods."""
+    mu, a = 398600.435436, 20000.0
+    period = 2.0 * math.pi * math.sqrt(a ** 3 / mu)
+    y0 = [-5007.248417988539, -1444.918140151374, 3628.534606178356, 0.717716656891, -10.224093784269,
+          0.748229399696]
+    cfg = oracle.config_new(A.DOPRI5, 0.0, 5.0 * period, 60.0, 1e-10, 1e-10)
+    o = _one("kepler", cfg, y0, [mu], cap=0)
+    assert (o.num_eval[0], o.accepted[0], o.rejected[0], o.out_count[0]) == (8145, 1339, 18, 2346)
+    assert tuple(o.y_final[:, 0]) == (-5007.248459071929, -1444.9175767267636, 3628.53456600154,
+                                      0.7177162284560319, -10.224093906800825, 0.7482297100304597)
+    cfg = oracle.config_new(A.DOP853, 0.0, 5.0 * period, 60.0, 1e-10, 1e-10)
+    o = _one("kepler", cfg, y0, [mu], cap=0)
+    assert (o.num_eval[0], o.accepted[0], o.rejected[0], o.out_count[0]) == (4722, 253, 84, 2346)
+
+
+def test_robertson_and_ball_fixtures():
+    """examples/chemical_reaction.rs:12-18 literal; examples/bouncing_ball.rs in f64 (Rk4 h = 0.01)."""
+    cfg = oracle.config_new(A.DOP853, 0.0, 0.3, 0.3, 1e-2, 1e-6)
+    o = _one("robertson", cfg, [1.0, 0.0, 0.0], [0.04, 1.0e4, 3.0e7], cap=0)
+    assert (o.num_eval[0], o.accepted[0], o.rejected[0], o.out_count[0]) == (2098, 103, 50, 2)
+    assert tuple(o.y_final[:, 0]) == (0.9886737692266352, 3.4503275486359126e-05, 0.011291727497878943)
+    o = _one("bouncing_ball", oracle.config_rk4(0.0, 10.0, 0.01), [10.0, 0.0, 0.0], [9.81], cap=0)
+    assert (o.num_eval[0], o.accepted[0], o.out_count[0]) == (572, 143, 144)
+    assert o.x_final[0] == 1.430000000000001
+    assert tuple(o.y_final[:, 0]) == (-0.03023450000000058, -14.02830000000002, 0.0)
+
+
+def test_cr3bp_example_fixture():
+    """examples/three_body_system.rs:17-25 literal: Dop853 1e-14, dx = 0.002, 0 -> 150."""
+    cfg = oracle.config_new(A.DOP853, 0.0, 150.0, 0.002, 1e-14, 1e-14)
+    o = _one("cr3bp", cfg, [-0.271, -0.42, 0.0, 0.3, -1.0, 0.0], [0.012300118882173], cap=0)
+    assert (o.num_eval[0], o.accepted[0], o.rejected[0], o.out_count[0]) == (129654, 8474, 231, 75001)
+    assert tuple(o.y_final[:, 0]) == (0.38237697246428154, -0.6300497681904966, 0.0, 0.19966199753987168,
+                                      -0.07418622375983154, 0.0)
+
+
+# ---------------------------------------------------------------- error paths (untested by the reference)
+def test_error_statuses():
+    cfg = oracle.config_from_param(A.DOPRI5, 0.0, 20.0, 0.1, 1e-6, 1e-6, 0.9, 0.04, 0.2, 10.0, 20.0, 0.0, 50, 1000,
+                                   A.OUT_SPARSE)
+    o = _one("lorenz", cfg, [1.0, 1.0, 1.0], LOR, cap=0)
+    assert o.status[0] == A.MAX_NUM_STEP_REACHED and o.n_step[0] == 51  # '>' (Q2): 51 attempts
+    cfg = oracle.config_from_param(A.DOP853, 0.0, 20.0, 0.1, 1e-6, 1e-6, 0.9, 0.0, 0.333, 6.0, 20.0, 0.0, 50, 1000,
+                                   A.OUT_SPARSE)
+    o = _one("lorenz", cfg, [1.0, 1.0, 1.0], LOR, cap=0)
+    assert o.status[0] == A.MAX_NUM_STEP_REACHED and o.n_step[0] == 50  # '>=' (Q2)
+    # Robertson over a long span with a frequent stiffness test -> StiffnessDetected
+    cfg = oracle.config_from_param(A.DOPRI5, 0.0, 40.0, 1.0, 1e-6, 1e-8, 0.9, 0.04, 0.2, 10.0, 40.0, 0.0, 100000, 10,
+                                   A.OUT_SPARSE)
+    o = _one("robertson", cfg, [1.0, 0.0, 0.0], [0.04, 1.0e4, 3.0e7], cap=0)
+    assert o.status[0] == A.STIFFNESS_DETECTED
+    # n_stiff == 0: the reference panics on `% 0`
+    cfg.n_stiff = 0
+    o = _one("robertson", cfg, [1.0, 0.0, 0.0], [0.04, 1.0e4, 3.0e7], cap=0)
+    assert o.status[0] == A.UNSUPPORTED_DOMAIN

@@ -1,0 +1,82 @@
+#!/usr/bin/env python3
+"""Kernel-time micro-harness for tuning experiments: runs named workloads through the C ABI's
+host-buffer entry and prints the device time of the step-loop kernel (CUDA events inside the
+library). ODE_B200_LIB=<path> picks an alternative build of the library.
+
+usage: kbench.py [workload ...]   workloads: lorenz_dp5 lorenz_dp8 lorenz_rk4 kepler_dp8 kepler_dp5
+                                             cr3bp_dp8_dense lorenz_dp5_dense ball_dp5_dense ...
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+
+import ode_solvers_b200 as ob  # noqa: E402
+from ode_solvers_b200 import workloads as W  # noqa: E402
+
+
+def build(name, n):
+    if name == "lorenz_dp5":
+        y0, p = W.lorenz_ensemble(n)
+        return "lorenz", ob.config_new(ob.DOPRI5, 0.0, 20.0, 0.1, 1e-6, 1e-6, out_type=ob.OUT_SPARSE), y0, p, 0, 262
+    if name == "lorenz_dp8":
+        y0, p = W.lorenz_ensemble(n)
+        return "lorenz", ob.config_new(ob.DOP853, 0.0, 20.0, 0.1, 1e-6, 1e-6, out_type=ob.OUT_SPARSE), y0, p, 0, 616
+    if name == "lorenz_rk4":
+        y0, p = W.lorenz_ensemble(n)
+        return "lorenz", ob.config_rk4(0.0, 20.0, 1e-3), y0, p, 0, 75
+    if name == "lorenz_dp5_dense":
+        y0, p = W.lorenz_ensemble(n)
+        return "lorenz", ob.config_new(ob.DOPRI5, 0.0, 20.0, 0.1, 1e-6, 1e-6), y0, p, 203, 298
+    if name == "kepler_dp8":
+        y0, p = W.kepler_sweep(n)
+        return ("kepler", ob.config_new(ob.DOP853, 0.0, 5.0 * W.kepler_period(), 60.0, 1e-10, 1e-10,
+                                        out_type=ob.OUT_SPARSE), y0, p, 0, 1120)
+    if name == "kepler_dp5":
+        y0, p = W.kepler_sweep(n)
+        return ("kepler", ob.config_new(ob.DOPRI5, 0.0, 5.0 * W.kepler_period(), 60.0, 1e-10, 1e-10,
+                                        out_type=ob.OUT_SPARSE), y0, p, 0, 487)
+    if name == "cr3bp_dp8_dense":
+        y0, p = W.cr3bp_ensemble(n)
+        return "cr3bp", ob.config_new(ob.DOP853, 0.0, 20.0, 0.5, 1e-12, 1e-12), y0, p, 43, 1395
+    if name == "threebody18_dp8":
+        y0, p = W.threebody18_ensemble(n)
+        return ("threebody18", ob.config_new(ob.DOP853, 0.0, 5.0, 0.1, 1e-9, 1e-9, out_type=ob.OUT_SPARSE), y0, p, 0,
+                3708)
+    if name == "robertson_dp8":
+        y0, p = W.robertson_sweep(n)
+        return ("robertson", ob.config_new(ob.DOP853, 0.0, 0.3, 0.3, 1e-2, 1e-6, out_type=ob.OUT_SPARSE), y0, p, 0,
+                638)
+    if name == "ball_dp5_dense":
+        y0, p = W.bouncing_ball_ensemble(n)
+        return "bouncing_ball", ob.config_new(ob.DOPRI5, 0.0, 10.0, 0.01, 1e-2, 1e-6), y0, p, 1003, 250
+    raise SystemExit("unknown workload " + name)
+
+
+def main():
+    names = sys.argv[1:] or ["lorenz_dp5", "lorenz_dp8", "kepler_dp8"]
+    n = int(os.environ.get("KBENCH_N", 1 << 20))
+    reps = int(os.environ.get("KBENCH_REPS", 3))
+    peak, _ = ob.measure_fp64_peak(0)
+    ctx = ob.default_context(0)
+    for q in (1, 0) if os.environ.get("KBENCH_STATIC") else (1,):
+        ctx.set_work_queue(bool(q))
+        for name in names:
+            nn = n if "threebody" not in name and "dense" not in name else min(n, 1 << 18)
+            sysname, cfg, y0, p, cap, flops = build(name, nn)
+            f = ob.System.builtin(sysname)
+            best = 1e30
+            for _ in range(reps):
+                o = ob.integrate_batch(f, cfg, y0, p, out_cap=cap, ctx=ctx)
+                best = min(best, o.kernel_ms)
+            acc, att = int(o.accepted.sum()), int(o.n_step.sum())
+            print("%-18s queue=%d n=%d kernel %.3f ms  %.3e acc-steps/s  %.2f TFLOP/s alg (%.1f%% of unfused FP64 "
+                  "peak)  acc/att=%d/%d bad=%d" % (name, q, nn, best, acc / best * 1e3, flops * att / best / 1e9,
+                                                 100 * flops * att / (best * 1e-3) / peak, acc, att,
+                                                 int((o.status != 0).sum())), flush=True)
+
+
+if __name__ == "__main__":
+    main()
