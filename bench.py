@@ -269,15 +269,9 @@ def run_native(args):
     assert acc_e2e == accepted, "e2e and device paths disagree"
 
     # ---- reduce over ranks: max time, sum work
-    if dist is not None:
-        t = torch.tensor([my_ms, e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        w = torch.tensor([accepted, attempts, n_bad], dtype=torch.int64, device=dev)
-        dist.all_reduce(w, op=dist.ReduceOp.SUM)
-        my_ms, e2e_s = float(t[0]), float(t[1])
-        tot_acc, tot_att, n_bad = int(w[0]), int(w[1]), int(w[2])
-    else:
-        tot_acc, tot_att = accepted, attempts
+    from ode_solvers_b200 import sharding
+    my_ms, (tot_acc, tot_att, n_bad) = sharding.reduce_report(dist, dev, my_ms, [accepted, attempts, n_bad])
+    e2e_s, _ = sharding.reduce_report(dist, dev, e2e_s, [0])
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
