@@ -275,7 +275,7 @@ def run_native(args):
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
-        return 0
+        return None
 
     ms_per_step = my_ms / args.steps
     value = tot_acc / (ms_per_step * 1e-3)
@@ -328,10 +328,26 @@ def run_native(args):
         "trajectories_not_ok": n_bad,
         "step_ms": [round(v, 4) for v in step_ms],
     }
-    print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
-    return 0
+    return line
+
+
+class QuietStdout:
+    """Route fd 1 to stderr while libraries initialise (NCCL prints its version banner to stdout),
+    so that the ONE JSON line is the only thing on stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
 
 
 def main():
@@ -348,7 +364,11 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
-    return run_native(args)
+    with QuietStdout():
+        line = run_native(args)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    return 0
 
 
 if __name__ == "__main__":
