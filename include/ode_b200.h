@@ -237,6 +237,9 @@ double ode_b200_tableau(const char* which, int i, int j);
 /* evaluate the device pow()/exp() clones on the GPU for n inputs (host pointers) */
 int ode_b200_debug_pow(ode_b200_ctx* ctx, int64_t n, const double* x, const double* y, double* out);
 int ode_b200_debug_exp(ode_b200_ctx* ctx, int64_t n, const double* x, double* out);
+/* the kernels' interleavable IEEE division (must equal a[i] / b[i] bit for bit) */
+int ode_b200_debug_div(ode_b200_ctx* ctx, int64_t n, const double* a, const double* b, double* out,
+                       int shared_denominator);
 
 #ifdef __cplusplus
 }

@@ -119,7 +119,7 @@ ABI_SYMBOLS = [
     "ode_b200_stream",
     "ode_b200_integrate_batch", "ode_b200_integrate_batch_device", "ode_b200_integrate_batch_multi",
     "ode_b200_set_work_queue", "ode_b200_com_evaluate",
-    "ode_b200_tableau", "ode_b200_debug_pow", "ode_b200_debug_exp",
+    "ode_b200_tableau", "ode_b200_debug_pow", "ode_b200_debug_exp", "ode_b200_debug_div",
 ]
 
 _lib = None
@@ -197,6 +197,8 @@ def load():
     lib.ode_b200_debug_pow.restype = C.c_int
     lib.ode_b200_debug_exp.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     lib.ode_b200_debug_exp.restype = C.c_int
+    lib.ode_b200_debug_div.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    lib.ode_b200_debug_div.restype = C.c_int
     _lib = lib
     return lib
 

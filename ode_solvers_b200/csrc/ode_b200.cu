@@ -701,6 +701,19 @@ __global__ void debug_pow_kernel(long long n, const double* x, const double* y, 
     if (i < n) o[i] = y ? pow_d(x[i], y[i]) : exp_d(x[i]);
 }
 
+__global__ void debug_div_kernel(long long n, const double* a, const double* b, double* o, int shared_den) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (shared_den) { /* one reciprocal for two numerators, as the kernels use it */
+        const double y = div_rcp_(b[i]);
+        const bool ok = div_in_range_(b[i]);
+        const double q1 = div_with_rcp_(a[i], b[i], y, ok), q2 = div_with_rcp_(-a[i], b[i], y, ok);
+        o[i] = (q1 == -q2 || (q1 != q1 && q2 != q2)) ? q1 : __longlong_as_double(0x7ff8dead00000000LL);
+    } else {
+        o[i] = div_(a[i], b[i]);
+    }
+}
+
 static int debug_fn(ode_b200_ctx* c, int64_t n, const double* x, const double* y, double* o) {
     if (!c) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
     if (n <= 0) return ODE_B200_SUCCESS;
@@ -722,6 +735,26 @@ static int debug_fn(ode_b200_ctx* c, int64_t n, const double* x, const double* y
 extern "C" int ode_b200_debug_pow(ode_b200_ctx* c, int64_t n, const double* x, const double* y, double* o) {
     if (!x || !y || !o) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "NULL pointer");
     return debug_fn(c, n, x, y, o);
+}
+extern "C" int ode_b200_debug_div(ode_b200_ctx* c, int64_t n, const double* a, const double* b, double* o,
+                                  int shared_den) {
+    if (!c) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    if (!a || !b || !o) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "NULL pointer");
+    if (n <= 0) return ODE_B200_SUCCESS;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (ensure(c, c->scratch0, n * 8) || ensure(c, c->scratch1, n * 8) || ensure(c, c->scratch2, n * 8))
+        return ODE_B200_ERR_CUDA;
+    cudaStream_t st = c->stream;
+    CUDA_TRY(cudaMemcpyAsync(c->scratch0.p, a, n * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(c->scratch1.p, b, n * 8, cudaMemcpyHostToDevice, st));
+    debug_div_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, (const double*)c->scratch0.p,
+                                                                  (const double*)c->scratch1.p,
+                                                                  (double*)c->scratch2.p, shared_den);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(o, c->scratch2.p, n * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return ODE_B200_SUCCESS;
 }
 extern "C" int ode_b200_debug_exp(ode_b200_ctx* c, int64_t n, const double* x, double* o) {
     if (!x || !o) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "NULL pointer");

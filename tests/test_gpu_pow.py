@@ -72,3 +72,37 @@ def test_exp():
     x = np.concatenate([rng.uniform(-5, 5, 200_000), rng.uniform(-750, 720, 200_000),
                         [0.0, -0.0, np.inf, -np.inf, np.nan, 1e-20, -1e-20, 709.78, 709.79, -745.1, -745.2]])
     assert same_f64(_dev_exp(x), _libm_exp(x)).all()
+
+
+def _dev_div(a, b, shared=0):
+    lib = _abi.load()
+    ctx = ob.default_context(0)
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(np.broadcast_to(b, a.shape), dtype=np.float64)
+    out = np.zeros_like(a)
+    assert lib.ode_b200_debug_div(ctx.handle, a.size, a.ctypes.data, b.ctypes.data, out.ctypes.data, shared) == 0
+    return out
+
+
+def test_div_matches_ieee():
+    """the kernels' interleavable division must be the correctly rounded IEEE quotient (what
+    Rust's `/` and the oracle's `/` produce) for every operand class"""
+    rng = np.random.default_rng(6)
+    n = 20_000_000
+    with np.errstate(all="ignore"):
+        for rep in range(5):
+            # random mantissas over a wide exponent range (inside and outside the fast window)
+            a = np.ldexp(rng.uniform(1, 2, n), rng.integers(-1070, 1023, n)) * rng.choice([-1.0, 1.0], n)
+            b = np.ldexp(rng.uniform(1, 2, n), rng.integers(-1070, 1023, n)) * rng.choice([-1.0, 1.0], n)
+            if rep >= 2:  # typical solver magnitudes
+                a = rng.standard_normal(n) * 10 ** rng.uniform(-12, 6, n)
+                b = rng.uniform(1e-12, 1e3, n)
+            if rep == 4:  # hard cases: mantissas at the ends, near-ties
+                a = np.ldexp(1 + rng.integers(0, 8, n) * 2.0 ** -52, rng.integers(-300, 300, n))
+                b = np.ldexp(2 - rng.integers(1, 8, n) * 2.0 ** -52, rng.integers(-300, 300, n))
+            assert same_f64(_dev_div(a, b), a / b).all()
+            assert same_f64(_dev_div(a, b, shared=1), a / b).all()
+        sp = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 5e-324, 2.2e-308, 1.7e308, 3.0, 1e-200, 1e200,
+                       -7.5, 0.9])
+        A, B = np.meshgrid(sp, sp)
+        assert same_f64(_dev_div(A.ravel(), B.ravel()), A.ravel() / B.ravel()).all()
