@@ -472,7 +472,10 @@ struct Dop853Stepper {
             const double eb = ((bsum[i] - k[0][i] * c_dp8_bhh[0]) - k[8][i] * c_dp8_bhh[1]) -
                               k[11][i] * c_dp8_bhh[2];
             const double sc = cfg.atol + fmax(fabs(s.y[i]), fabs(y8[i])) * cfg.rtol;
-            const double q1 = ee / sc, q2 = eb / sc;
+            /* err_est_i / sc_i and err_bhh_i / sc_i: one refined reciprocal, two exact quotients */
+            const double rsc = div_rcp_(sc);
+            const bool sc_ok = div_in_range_(sc);
+            const double q1 = div_with_rcp_(ee, sc, rsc, sc_ok), q2 = div_with_rcp_(eb, sc, rsc, sc_ok);
             err += q1 * q1;
             err2 += q2 * q2;
         }

@@ -35,12 +35,15 @@ struct SysKepler {
     ODE_DEV static void rhs(double, const double* y, double* dy, const double* p) {
         const double r = sqrt(y[0] * y[0] + y[1] * y[1] + y[2] * y[2]);
         const double r3 = r * r * r;
+        /* three exact IEEE quotients by the same r3: one refined reciprocal (ode_device.cuh) */
+        const double ir3 = div_rcp_(r3);
+        const bool ok = div_in_range_(r3);
         dy[0] = y[3];
         dy[1] = y[4];
         dy[2] = y[5];
-        dy[3] = -p[0] * y[0] / r3;
-        dy[4] = -p[0] * y[1] / r3;
-        dy[5] = -p[0] * y[2] / r3;
+        dy[3] = div_with_rcp_(-p[0] * y[0], r3, ir3, ok);
+        dy[4] = div_with_rcp_(-p[0] * y[1], r3, ir3, ok);
+        dy[5] = div_with_rcp_(-p[0] * y[2], r3, ir3, ok);
     }
     ODE_DEV static bool solout(double, const double*, const double*, const double*) { return false; }
 };
