@@ -30,10 +30,33 @@ namespace ode_b200 {
 
 
 
+/*
+ * Resident CTAs per SM the register allocator must leave room for (Stepper::kMinBlocks).
+ * The step loop is bound by dependent FP64 latency (ncu: "wait" is the top stall), so for small
+ * states warps per scheduler matter more than a few spilled scalars; for n = 6 the balance
+ * moves towards registers. Measured on B200, 2^20 trajectories, kernel ms at 2/3/4/5/6 CTAs:
+ *   Lorenz  Dopri5  46.4 / 36.2 / 32.4 / 31.4 / 31.8      Lorenz  Dop853  28.9 / 23.7 / 22.2 / 21.7 / 22.7
+ *   Kepler  Dopri5 133.3 /113.4 /105.9 /109.7 /118.6      Kepler  Dop853  55.2 / 67.0 / 64.2 / 60.0 / 62.1
+ *   CR3BP Dop853 Dense (2^18) 63.3 / 58.6 / 55.4 / 69.5 / 102.2      3-body-18 Dop853 (2^18) 18.9 / 18.0 / 18.1 / - / 26.1
+ * -DODE_B200_MIN_BLOCKS=k overrides the table for such sweeps.
+ */
+template <int N, int METHOD, bool DENSE>
+constexpr int min_blocks_for() {
+#ifdef ODE_B200_MIN_BLOCKS
+    return ODE_B200_MIN_BLOCKS;
+#else
+    if (N <= 4) return 5;
+    if (N > 8) return 3;
+    if (METHOD == ODE_B200_DOP853) return DENSE ? 4 : 2;
+    return 4;
+#endif
+}
+
 /* ============================================================================ Rk4 */
 template <class Sys>
 struct Rk4Stepper {
     static constexpr int N = Sys::DIM;
+    static constexpr int kMinBlocks = min_blocks_for<N, ODE_B200_RK4, false>();
     struct State {
         double y[N];
         double p[Sys::NP > 0 ? Sys::NP : 1];
@@ -109,6 +132,7 @@ struct Dopri5Stepper {
     static constexpr bool DENSE = OUT == ODE_B200_OUT_DENSE;
     static constexpr bool CONT = OUT == ODE_B200_OUT_CONTINUOUS;
     static constexpr bool TRACK_LAST = DENSE && Sys::HAS_SOLOUT;
+    static constexpr int kMinBlocks = min_blocks_for<N, ODE_B200_DOPRI5, DENSE || CONT>();
 
     struct State {
         double y[N], k0[N]; /* k0 = f(x, y): first-same-as-last slot k[0] */
@@ -339,6 +363,7 @@ struct Dop853Stepper {
     static constexpr int N = Sys::DIM;
     static constexpr bool DENSE = OUT == ODE_B200_OUT_DENSE;
     static constexpr bool TRACK_LAST = DENSE && Sys::HAS_SOLOUT;
+    static constexpr int kMinBlocks = min_blocks_for<N, ODE_B200_DOP853, DENSE>();
 
     struct State {
         double y[N], k0[N]; /* k0 = reference k[0] = f(x, y) */
@@ -657,23 +682,8 @@ struct Dop853Stepper {
 };
 
 /* ============================================================================ kernels */
-/*
- * Resident CTAs per SM the register allocator must leave room for. The step loop is bound by
- * dependent FP64 latency (ncu: "wait" is the top stall), so warps per scheduler matter more
- * than a few spilled scalars: 5 CTAs x 4 warps (<= 96 registers) measured 31.4 ms against
- * 46.4 ms at 255 registers and 32.7 ms at 126 for the 2^20-trajectory Lorenz/Dopri5 run, and
- * 70.8 ms against 96.1 ms for Kepler/Dop853 (profiles/r1_notes.md).
- */
-#ifdef ODE_B200_MIN_BLOCKS
-template <int N>
-constexpr int min_blocks_for_dim() { return ODE_B200_MIN_BLOCKS; }
-#else
-template <int N>
-constexpr int min_blocks_for_dim() { return N <= 8 ? 5 : 2; }
-#endif
-
 template <class Stepper>
-__global__ void __launch_bounds__(kBlockThreads, min_blocks_for_dim<Stepper::N>()) ode_step_loop_kernel(const __grid_constant__ KernelArgs a) {
+__global__ void __launch_bounds__(kBlockThreads, Stepper::kMinBlocks) ode_step_loop_kernel(const __grid_constant__ KernelArgs a) {
     run_lanes_<Stepper>(a);
 }
 
