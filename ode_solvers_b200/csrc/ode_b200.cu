@@ -353,6 +353,15 @@ static int launch_device(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg
     ka.facc2 = 1.0 / cfg->fac_max;
     ka.h_max_abs = fabs(cfg->h_max);
     ka.posneg = (cfg->x_end - cfg->x0) > 0.0 ? 1.0 : -1.0; /* sign(1, x_end - x) */
+#ifndef __CUDA_ARCH__ /* host pass only: the host tables do not exist in the device pass */
+    {
+        /* fac_old.powf(-beta) at fac_old's floor 1e-4, through the SAME clone the kernels run
+         * (host build of ode_pow.h; equal to libm pow bit for bit, tests/test_pow_clone.py) */
+        const ode_pow_tabs T = ode_pow_host_tabs();
+        ka.pw_floor = cfg->beta == 0.0 ? 1.0 : ode_pow(1.0E-4, -cfg->beta, T);
+        ka.pow_shared_log = ode_pow_y_is_plain_(cfg->alpha) && (cfg->beta == 0.0 || ode_pow_y_is_plain_(-cfg->beta));
+    }
+#endif
     ka.n_traj = n;
     ka.y0 = y0;
     ka.params = params;

@@ -18,6 +18,9 @@ struct KernelArgs {
     double facc2;               /* 1 / fac_max */
     double h_max_abs;           /* |h_max| */
     double posneg;              /* sign(1, x_end - x) */
+    double pw_floor;            /* pow(1e-4, -beta): fac_old.powf(-beta) while fac_old sits at its floor;
+                                   host libm == device clone bit for bit, 1.0 for beta == 0 */
+    int pow_shared_log;         /* alpha and -beta are in pow's main exponent range (always, for sane configs) */
     long long n_traj;
     const double* y0;           /* SoA [dim][n_traj] */
     const double* params;       /* [n_params] or SoA [n_params][n_traj] */

@@ -156,7 +156,7 @@ struct Dopri5Stepper {
         load_traj_<Sys>(a, t, s.y, s.p);
         s.x = s.x_old = s.xd = a.cfg.x0;
         counters_init_(s.c);
-        ctrl_init_(s.ctrl);
+        ctrl_init_(s.ctrl, a);
         s.iasti = s.non_stiff = s.stiff_ctr = 0;
         s.h = a.cfg.h0;
         if (s.h == 0.0) {
@@ -399,7 +399,7 @@ struct Dop853Stepper {
         load_traj_<Sys>(a, t, s.y, s.p);
         s.x = s.x_old = s.xd = a.cfg.x0;
         counters_init_(s.c);
-        ctrl_init_(s.ctrl);
+        ctrl_init_(s.ctrl, a);
         s.iasti = s.non_stiff = s.stiff_ctr = 0;
         s.h = a.cfg.h0;
         if (s.h == 0.0) {

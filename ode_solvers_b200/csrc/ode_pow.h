@@ -239,16 +239,8 @@ ODE_POW_SLOW int ode_pow_special_(double x, double y, ode_u64* pix, ode_u32* psi
     return 0;
 }
 
-/* pow(x, y), bit-identical to glibc 2.39 x86-64 (FMA variant). */
-ODE_POW_FN double ode_pow(double x, double y, ode_pow_tabs T) {
-    ode_u32 sign_bias = 0;
-    ode_u64 ix = ODE_ASU64(x);
-    ode_u32 topx = (ode_u32)(ix >> 52), topy = (ode_u32)(ODE_ASU64(y) >> 52);
-    if (topx - 0x001u >= 0x7ffu - 0x001u || (topy & 0x7ff) - 0x3beu >= 0x43eu - 0x3beu) {
-        double res;
-        if (ode_pow_special_(x, y, &ix, &sign_bias, &res)) return res;
-    }
-    /* log_inline: log(x) = hi + lo */
+/* log(x) = *hi + *lo in double-double for ix = bits of a positive NORMAL x (log_inline). */
+ODE_POW_FN void ode_pow_log_(ode_u64 ix, ode_pow_tabs T, double* phi, double* plo) {
     ode_u64 tmp = ix - ODE_POW_OFF;
     int i = (int)((tmp >> 45) & 127u);
     int k = (int)((ode_i64)tmp >> 52);
@@ -271,11 +263,39 @@ ODE_POW_FN double ode_pow(double x, double y, ode_pow_tabs T) {
     q = fma(ar2, q, fma(r, K_A2, K_A1));
     double lo = fma(ar3, q, lo1 + lo2 + lo3 + lo4);
     double y1 = hi + lo;
-    double ltail = hi - y1 + lo;
-    /* y * log(x) in double-double */
-    double ehi = y * y1;
-    double elo = fma(y, ltail, fma(y, y1, -ehi));
+    *phi = y1;
+    *plo = hi - y1 + lo;
+}
+
+/* exp(y * (hi + lo)) with the product in double-double: the second half of pow. Given the
+ * log of one x it yields pow(x, y) for ANY y in pow's main range, so a caller that needs
+ * pow(x, y1) and pow(x, y2) (the PI controller: err^alpha now, err^-beta for the next step)
+ * pays for one log only -- same operations on the same values, hence the same bits. */
+ODE_POW_FN double ode_pow_exp_(double y, double lhi, double llo, ode_u32 sign_bias, ode_pow_tabs T) {
+    double ehi = y * lhi;
+    double elo = fma(y, llo, fma(y, lhi, -ehi));
     return ode_exp_inline_(ehi, elo, sign_bias, 1, T);
+}
+
+/* true when pow(x, y) takes the main path for this x: positive, normal, finite */
+ODE_POW_FN int ode_pow_x_is_plain_(double x) { return (ode_u32)(ODE_ASU64(x) >> 52) - 0x001u < 0x7ffu - 0x001u; }
+/* true when pow(x, y) takes the main path for this y: 2^-65 <= |y| < 2^63 */
+ODE_POW_FN int ode_pow_y_is_plain_(double y) {
+    return ((ode_u32)(ODE_ASU64(y) >> 52) & 0x7ff) - 0x3beu < 0x43eu - 0x3beu;
+}
+
+/* pow(x, y), bit-identical to glibc 2.39 x86-64 (FMA variant). */
+ODE_POW_FN double ode_pow(double x, double y, ode_pow_tabs T) {
+    ode_u32 sign_bias = 0;
+    ode_u64 ix = ODE_ASU64(x);
+    ode_u32 topx = (ode_u32)(ix >> 52), topy = (ode_u32)(ODE_ASU64(y) >> 52);
+    if (topx - 0x001u >= 0x7ffu - 0x001u || (topy & 0x7ff) - 0x3beu >= 0x43eu - 0x3beu) {
+        double res;
+        if (ode_pow_special_(x, y, &ix, &sign_bias, &res)) return res;
+    }
+    double lhi, llo;
+    ode_pow_log_(ix, T, &lhi, &llo);
+    return ode_pow_exp_(y, lhi, llo, sign_bias, T);
 }
 
 /* exp(x), bit-identical to glibc 2.39 x86-64 (FMA variant). */
