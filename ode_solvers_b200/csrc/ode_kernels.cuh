@@ -311,7 +311,9 @@ struct Dopri5Stepper {
                     if constexpr (Sys::HAS_SOLOUT) {
                         if (Sys::solout(s.xd, s.ylast, s.k0, s.p)) break;
                     }
-                    if (!pushed || s.c.out_count > (1u << 30)) { unsupported = true; break; } /* reference never returns */
+                    /* the reference never returns: nothing changes between passes once no sample is
+                     * pushed, or when dx == 0 leaves xd where it was */
+                    if (!pushed || cfg.dx == 0.0 || s.c.out_count > (1u << 26)) { unsupported = true; break; }
                 }
                 if (unsupported) return finish(s, a, ODE_B200_UNSUPPORTED_DOMAIN);
                 if (fabs(s.xd - cfg.x_end) < 1.0e-9) { /* endpoint rule, dopri5.rs:472-478 (Q9) */
@@ -639,7 +641,7 @@ struct Dop853Stepper {
                                 for (int i = 0; i < N; ++i) s.ylast[i] = yo[i];
                             }
                             s.xd += cfg.dx;
-                            if (s.c.out_count > (1u << 30)) { unsupported = true; break; }
+                            if (s.c.out_count > (1u << 26)) { unsupported = true; break; }
                         } else { /* the reference never leaves this loop */
                             unsupported = true;
                             break;

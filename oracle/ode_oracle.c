@@ -167,7 +167,7 @@ typedef struct {
     double com_lower;
 } traj_result_t;
 
-#define DENSE_GUARD (1u << 30)
+#define DENSE_GUARD (1u << 26)
 
 /* ------------------------------------------------------------------ hinit */
 
@@ -390,7 +390,9 @@ static void dopri5_integrate(const ode_oracle_system* S, const ode_b200_config* 
                     }
                     if (sink->count == 0) { bad = 1; break; } /* reference: unwrap() on empty -> panic */
                     if (S->solout && S->solout(xd, sink->last, k[0], p)) break;
-                    if (!pushed || ++guard > DENSE_GUARD) { bad = 1; break; } /* reference: infinite loop */
+                    /* reference: infinite loop (nothing changes between passes once no sample is
+                     * pushed, or when dx == 0 leaves xd where it was) */
+                    if (!pushed || dx == 0.0 || ++guard > DENSE_GUARD) { bad = 1; break; }
                 }
                 if (bad) {
                     R->status = ODE_B200_UNSUPPORTED_DOMAIN;

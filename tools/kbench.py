@@ -30,6 +30,16 @@ def build(name, n):
     if name == "lorenz_dp5_dense":
         y0, p = W.lorenz_ensemble(n)
         return "lorenz", ob.config_new(ob.DOPRI5, 0.0, 20.0, 0.1, 1e-6, 1e-6), y0, p, 203, 298
+    if name == "lorenz_dp5_dense_hbm":  # dense-output-heavy: 2001 samples x 32 B per trajectory
+        y0, p = W.lorenz_ensemble(n)
+        return "lorenz", ob.config_new(ob.DOPRI5, 0.0, 20.0, 0.01, 1e-6, 1e-6), y0, p, 2003, 298
+    if name == "lorenz_rk4_all_steps":  # every step recorded: 2001 x 32 B per trajectory
+        y0, p = W.lorenz_ensemble(n)
+        return "lorenz", ob.config_rk4(0.0, 2.0, 1e-3), y0, p, 2002, 75
+    if name == "lorenz_dp5_com":        # ContinuousOutputModel: 136 B per accepted step
+        y0, p = W.lorenz_ensemble(n)
+        return ("lorenz", ob.config_new(ob.DOPRI5, 0.0, 20.0, 0.1, 1e-6, 1e-6, out_type=ob.OUT_CONTINUOUS), y0, p,
+                -1000, 298)
     if name == "kepler_dp8":
         y0, p = W.kepler_sweep(n)
         return ("kepler", ob.config_new(ob.DOP853, 0.0, 5.0 * W.kepler_period(), 60.0, 1e-10, 1e-10,
@@ -64,13 +74,22 @@ def main():
     for q in (1, 0) if os.environ.get("KBENCH_STATIC") else (1,):
         ctx.set_work_queue(bool(q))
         for name in names:
-            nn = n if "threebody" not in name and "dense" not in name else min(n, 1 << 18)
+            nn = n if not any(k in name for k in ("threebody", "dense", "all_steps", "com")) else min(n, 1 << 18)
             sysname, cfg, y0, p, cap, flops = build(name, nn)
             f = ob.System.builtin(sysname)
             best = 1e30
+            com_cap = -cap if cap < 0 else 0
+            cap = abs(cap)
             for _ in range(reps):
-                o = ob.integrate_batch(f, cfg, y0, p, out_cap=cap, ctx=ctx)
+                o = ob.integrate_batch(f, cfg, y0, p, out_cap=cap, com_cap=com_cap, ctx=ctx)
                 best = min(best, o.kernel_ms)
+            if cap:
+                dim = y0.shape[0]
+                stored = int(np.minimum(o.out_count, cap).sum()) * (1 + dim) * 8
+                if com_cap:
+                    stored += int(np.minimum(o.com_count, com_cap).sum()) * (5 * dim + 2) * 8
+                print("   output bytes written %.3f GB -> %.1f GB/s of HBM write (algorithmic)" % (
+                    stored / 1e9, stored / 1e9 / (best * 1e-3)))
             acc, att = int(o.accepted.sum()), int(o.n_step.sum())
             print("%-18s queue=%d n=%d kernel %.3f ms  %.3e acc-steps/s  %.2f TFLOP/s alg (%.1f%% of unfused FP64 "
                   "peak)  acc/att=%d/%d bad=%d" % (name, q, nn, best, acc / best * 1e3, flops * att / best / 1e9,
