@@ -45,7 +45,7 @@ constexpr int min_blocks_for() {
 #ifdef ODE_B200_MIN_BLOCKS
     return ODE_B200_MIN_BLOCKS;
 #else
-    if (N <= 4) return 5;
+    if (N <= 4) return DENSE ? 4 : 5; /* Dense/Continuous keep rcont[][] live: 96 registers spill */
     if (N > 8) return 3;
     if (METHOD == ODE_B200_DOP853) return DENSE ? 4 : 2;
     return 4;
