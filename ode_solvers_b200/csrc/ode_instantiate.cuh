@@ -11,14 +11,17 @@
 
 #define ODE_B200_KPTR(...) ((const void*)&ode_b200::ode_step_loop_kernel<__VA_ARGS__>)
 
-#define ODE_B200_DEFINE_SYSTEM(SYS, NAME)                                                               \
-    extern "C" const ode_b200::SystemEntry ode_b200_entry_##NAME = {                                    \
-        #NAME, ode_b200::SYS::DIM, ode_b200::SYS::NP, ode_b200::SYS::HAS_SOLOUT ? 1 : 0,                 \
-        {{ODE_B200_KPTR(ode_b200::Rk4Stepper<ode_b200::SYS>), ODE_B200_KPTR(ode_b200::Rk4Stepper<ode_b200::SYS>), \
-          ODE_B200_KPTR(ode_b200::Rk4Stepper<ode_b200::SYS>)},                                           \
-         {ODE_B200_KPTR(ode_b200::Dopri5Stepper<ode_b200::SYS, ODE_B200_OUT_DENSE>),                     \
-          ODE_B200_KPTR(ode_b200::Dopri5Stepper<ode_b200::SYS, ODE_B200_OUT_SPARSE>),                    \
-          ODE_B200_KPTR(ode_b200::Dopri5Stepper<ode_b200::SYS, ODE_B200_OUT_CONTINUOUS>)},               \
-         {ODE_B200_KPTR(ode_b200::Dop853Stepper<ode_b200::SYS, ODE_B200_OUT_DENSE>),                     \
-          ODE_B200_KPTR(ode_b200::Dop853Stepper<ode_b200::SYS, ODE_B200_OUT_SPARSE>),                    \
-          ODE_B200_KPTR(ode_b200::Dop853Stepper<ode_b200::SYS, ODE_B200_OUT_SPARSE>)}}};
+#define ODE_B200_KSET(SYS, ST)                                                                              \
+    {{ODE_B200_KPTR(ode_b200::Rk4Stepper<ode_b200::SYS, ST>), ODE_B200_KPTR(ode_b200::Rk4Stepper<ode_b200::SYS, ST>), \
+      ODE_B200_KPTR(ode_b200::Rk4Stepper<ode_b200::SYS, ST>)},                                               \
+     {ODE_B200_KPTR(ode_b200::Dopri5Stepper<ode_b200::SYS, ODE_B200_OUT_DENSE, ST>),                         \
+      ODE_B200_KPTR(ode_b200::Dopri5Stepper<ode_b200::SYS, ODE_B200_OUT_SPARSE, ST>),                        \
+      ODE_B200_KPTR(ode_b200::Dopri5Stepper<ode_b200::SYS, ODE_B200_OUT_CONTINUOUS, ST>)},                   \
+     {ODE_B200_KPTR(ode_b200::Dop853Stepper<ode_b200::SYS, ODE_B200_OUT_DENSE, ST>),                         \
+      ODE_B200_KPTR(ode_b200::Dop853Stepper<ode_b200::SYS, ODE_B200_OUT_SPARSE, ST>),                        \
+      ODE_B200_KPTR(ode_b200::Dop853Stepper<ode_b200::SYS, ODE_B200_OUT_SPARSE, ST>)}}
+
+#define ODE_B200_DEFINE_SYSTEM(SYS, NAME)                                                \
+    extern "C" const ode_b200::SystemEntry ode_b200_entry_##NAME = {                     \
+        #NAME, ode_b200::SYS::DIM, ode_b200::SYS::NP, ode_b200::SYS::HAS_SOLOUT ? 1 : 0, \
+        {ODE_B200_KSET(SYS, false), ODE_B200_KSET(SYS, true)}};

@@ -49,6 +49,7 @@ struct Api {
     CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
                              CUstream, void**, void**) = nullptr;
     CUresult (*Occupancy)(int*, CUfunction, int, size_t) = nullptr;
+    CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
     CUresult (*GetErrorName)(CUresult, const char**) = nullptr;
 };
 
@@ -93,6 +94,7 @@ Api& api() {
         L(drv, ModuleGetFunction, "cuModuleGetFunction")
         L(drv, LaunchKernel, "cuLaunchKernel")
         L(drv, Occupancy, "cuOccupancyMaxActiveBlocksPerMultiprocessor")
+        L(drv, FuncSetAttribute, "cuFuncSetAttribute")
         L(drv, GetErrorName, "cuGetErrorName")
 #undef L
         a.drv_ok = true;
@@ -109,15 +111,16 @@ struct Compiled {
     int per_sm = 0;
 };
 /* (system, device, method, out_type) -> loaded kernel */
-std::map<std::tuple<int, int, int, int>, Compiled> g_cache;
+std::map<std::tuple<int, int, int, int, int>, Compiled> g_cache;
 
-std::string stepper_expr(int method, int out_type) {
-    if (method == ODE_B200_RK4) return "ode_b200::Rk4Stepper<ode_b200::SysUser>";
+std::string stepper_expr(int method, int out_type, bool staged) {
+    const std::string st = staged ? ", true>" : ", false>";
+    if (method == ODE_B200_RK4) return "ode_b200::Rk4Stepper<ode_b200::SysUser" + st;
     if (method == ODE_B200_DOPRI5)
-        return "ode_b200::Dopri5Stepper<ode_b200::SysUser, " + std::to_string(out_type) + ">";
+        return "ode_b200::Dopri5Stepper<ode_b200::SysUser, " + std::to_string(out_type) + st;
     /* Dop853 treats Continuous like Sparse (dop853.rs:398,540-542) */
     const int o = out_type == ODE_B200_OUT_DENSE ? ODE_B200_OUT_DENSE : ODE_B200_OUT_SPARSE;
-    return "ode_b200::Dop853Stepper<ode_b200::SysUser, " + std::to_string(o) + ">";
+    return "ode_b200::Dop853Stepper<ode_b200::SysUser, " + std::to_string(o) + st;
 }
 
 std::string make_source(const JitSystem& s, const std::string& stepper) {
@@ -138,11 +141,11 @@ struct Cubin {
     std::string mangled;
 };
 /* (system, method, out_type) -> cubin; device independent */
-std::map<std::tuple<int, int, int>, Cubin> g_cubins;
+std::map<std::tuple<int, int, int, int>, Cubin> g_cubins;
 
-bool compile_cubin(const JitSystem& s, int method, int out_type, Cubin* out, std::string* err) {
+bool compile_cubin(const JitSystem& s, int method, int out_type, bool staged, Cubin* out, std::string* err) {
     Api& a = api();
-    const std::string stepper = stepper_expr(method, out_type);
+    const std::string stepper = stepper_expr(method, out_type, staged);
     const std::string src = make_source(s, stepper);
     const std::string name_expr = "ode_b200::ode_step_loop_kernel<" + stepper + " >";
     nvrtcProgram prog;
@@ -186,14 +189,14 @@ bool compile_cubin(const JitSystem& s, int method, int out_type, Cubin* out, std
 }
 
 /* g_mu held */
-const Cubin* get_cubin(int idx, const JitSystem& s, int method, int out_type, std::string* err) {
+const Cubin* get_cubin(int idx, const JitSystem& s, int method, int out_type, bool staged, std::string* err) {
     const int o = method == ODE_B200_RK4 ? 0 : (method == ODE_B200_DOP853 && out_type != ODE_B200_OUT_DENSE
                                                     ? ODE_B200_OUT_SPARSE : out_type);
-    auto key = std::make_tuple(idx, method, o);
+    auto key = std::make_tuple(idx, method, o, staged ? 1 : 0);
     auto it = g_cubins.find(key);
     if (it != g_cubins.end()) return &it->second;
     Cubin c;
-    if (!compile_cubin(s, method, out_type, &c, err)) return nullptr;
+    if (!compile_cubin(s, method, out_type, staged, &c, err)) return nullptr;
     return &(g_cubins[key] = std::move(c));
 }
 
@@ -231,7 +234,7 @@ int jit_register(const char* name, int dim, int n_params, const char* rhs_body, 
     return (int)g_systems.size() - 1;
 }
 
-bool jit_compile(int idx, int method, int out_type, std::string* err) {
+bool jit_compile(int idx, int method, int out_type, bool staged, std::string* err) {
     Api& a = api();
     if (!a.ok) {
         *err = "JIT unavailable: " + a.why;
@@ -243,7 +246,7 @@ bool jit_compile(int idx, int method, int out_type, std::string* err) {
         return false;
     }
     std::lock_guard<std::mutex> g(g_mu);
-    return get_cubin(idx, *s, method, out_type, err) != nullptr;
+    return get_cubin(idx, *s, method, out_type, staged, err) != nullptr;
 }
 
 const JitSystem* jit_system(int idx) {
@@ -252,8 +255,8 @@ const JitSystem* jit_system(int idx) {
     return g_systems[idx].get();
 }
 
-bool jit_launch(int idx, int device, int num_sms, int method, int out_type, const void* kernel_args,
-                size_t kernel_args_bytes, int block, long long blocks_all, int use_queue, void* stream,
+bool jit_launch(int idx, int device, int num_sms, int method, int out_type, bool staged, const void* kernel_args,
+                size_t kernel_args_bytes, int block, long long blocks_all, int use_queue, size_t dyn_smem, void* stream,
                 std::string* err) {
     (void)kernel_args_bytes;
     Api& a = api();
@@ -270,24 +273,27 @@ bool jit_launch(int idx, int device, int num_sms, int method, int out_type, cons
     {
         std::lock_guard<std::mutex> g(g_mu);
         const int o = method == ODE_B200_RK4 ? 0 : out_type;
-        auto key = std::make_tuple(idx, device, method, o);
+        auto key = std::make_tuple(idx, device, method, o, staged ? 1 : 0);
         auto it = g_cache.find(key);
         if (it == g_cache.end()) {
-            const Cubin* cb = get_cubin(idx, *s, method, out_type, err);
+            const Cubin* cb = get_cubin(idx, *s, method, out_type, staged, err);
             if (!cb || !load(*cb, &c, err)) return false;
-            if (a.Occupancy(&c.per_sm, c.fn, block, 0) != CUDA_SUCCESS || c.per_sm < 1) {
-                *err = "JIT kernel does not fit on an SM";
-                return false;
-            }
             g_cache[key] = c;
         } else {
             c = it->second;
         }
     }
+    if (dyn_smem > 48 * 1024) a.FuncSetAttribute(c.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)dyn_smem);
+    int per_sm = 0;
+    if (a.Occupancy(&per_sm, c.fn, block, dyn_smem) != CUDA_SUCCESS || per_sm < 1) {
+        *err = "JIT kernel does not fit on an SM";
+        return false;
+    }
     long long grid = blocks_all;
-    if (use_queue) grid = std::min<long long>(blocks_all, (long long)num_sms * c.per_sm);
+    if (use_queue) grid = std::min<long long>(blocks_all, (long long)num_sms * per_sm);
     void* args[] = {const_cast<void*>(kernel_args)};
-    CUresult cr = a.LaunchKernel(c.fn, (unsigned)grid, 1, 1, (unsigned)block, 1, 1, 0, (CUstream)stream, args, nullptr);
+    CUresult cr = a.LaunchKernel(c.fn, (unsigned)grid, 1, 1, (unsigned)block, 1, 1, (unsigned)dyn_smem,
+                                 (CUstream)stream, args, nullptr);
     if (cr != CUDA_SUCCESS) {
         const char* nm = "?";
         a.GetErrorName(cr, &nm);

@@ -24,11 +24,11 @@ int jit_register(const char* name, int dim, int n_params, const char* rhs_body, 
 const JitSystem* jit_system(int idx);
 
 /* NVRTC-compile one (method, out_type) kernel of a registered system to a cubin (no GPU needed) */
-bool jit_compile(int idx, int method, int out_type, std::string* err);
+bool jit_compile(int idx, int method, int out_type, bool staged, std::string* err);
 
 /* compile (once per system/device/method/out_type), size the grid and launch on `stream` */
-bool jit_launch(int idx, int device, int num_sms, int method, int out_type, const void* kernel_args,
-                size_t kernel_args_bytes, int block, long long blocks_all, int use_queue, void* stream,
+bool jit_launch(int idx, int device, int num_sms, int method, int out_type, bool staged, const void* kernel_args,
+                size_t kernel_args_bytes, int block, long long blocks_all, int use_queue, size_t dyn_smem, void* stream,
                 std::string* err);
 
 }  // namespace ode_b200

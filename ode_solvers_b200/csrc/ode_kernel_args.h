@@ -10,6 +10,23 @@ namespace ode_b200 {
 /* threads per CTA of every step-loop kernel (4 warps; the persistent grid is SMs x resident CTAs) */
 constexpr int kBlockThreads = 128;
 
+/*
+ * Output staging. The per-step results are trajectory-major (one trajectory's samples are
+ * contiguous, like the crate's Vec), so a warp whose 32 lanes each push one sample writes 32
+ * different 128-byte lines with 8-byte pieces (measured: 0.45-0.64 TB/s of useful writes).
+ * Instead every lane collects up to stage_samples(dim) samples in shared memory and the warp
+ * writes one lane's run at a time as contiguous 8-byte x 32 stores (full sectors). It costs
+ * shared memory (occupancy for n >= 6) and a ballot per pass, so it is a compile-time variant
+ * of every kernel (STAGE) that the launcher picks only for output-heavy calls (rule in ode_b200.cu).
+ * Lane buffer: x[R] then y[R][dim]; stride is odd so that 32 lanes hit 32 different bank pairs.
+ */
+__host__ __device__ constexpr int stage_samples(int dim) {
+    return 40 / (1 + dim) < 2 ? 2 : (40 / (1 + dim) > 8 ? 8 : 40 / (1 + dim));
+}
+__host__ __device__ constexpr int stage_stride(int dim) { return (stage_samples(dim) * (1 + dim)) | 1; }
+/* dynamic shared memory of a staging launch: per-thread {staged, base} + the lane buffers */
+__host__ __device__ constexpr int stage_smem_doubles(int dim) { return kBlockThreads * (1 + stage_stride(dim)); }
+
 struct KernelArgs {
     ode_b200_config cfg;        /* batch-uniform solver parameters (from_param argument list) */
     /* Controller::new's derived fields (controller.rs:29-49), computed once on the host with

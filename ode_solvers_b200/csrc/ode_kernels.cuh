@@ -53,9 +53,10 @@ constexpr int min_blocks_for() {
 }
 
 /* ============================================================================ Rk4 */
-template <class Sys>
+template <class Sys, bool STAGE = false>
 struct Rk4Stepper {
     static constexpr int N = Sys::DIM;
+    static constexpr bool kStage = STAGE;
     static constexpr int kMinBlocks = min_blocks_for<N, ODE_B200_RK4, false>();
     struct State {
         double y[N];
@@ -72,9 +73,9 @@ struct Rk4Stepper {
         s.traj = t;
         load_traj_<Sys>(a, t, s.y, s.p);
         s.x = a.cfg.x0;
-        counters_init_(s.c);
+        counters_init_<STAGE>(s.c);
         s.status = ODE_B200_OK;
-        push_<N>(a, t, s.c.out_count, s.x, s.y);
+        push_<N, STAGE>(a, t, s.c, s.x, s.y);
         const double ns = ceil((a.cfg.x_end - s.x) / a.cfg.step_size);
         if (!(ns >= 0.0) || ns > 4.0e9) { /* to_usize().unwrap() panics in the reference */
             s.status = ODE_B200_UNSUPPORTED_DOMAIN;
@@ -111,7 +112,7 @@ struct Rk4Stepper {
         s.x = x_new;
 #pragma unroll
         for (int i = 0; i < N; ++i) s.y[i] = yn[i];
-        push_<N>(a, s.traj, s.c.out_count, x_new, yn);
+        push_<N, STAGE>(a, s.traj, s.c, x_new, yn);
         s.c.num_eval += 4;
         s.c.accepted += 1;
         s.c.n_step += 1;
@@ -126,9 +127,10 @@ struct Rk4Stepper {
 };
 
 /* ============================================================================ Dopri5 */
-template <class Sys, int OUT>
+template <class Sys, int OUT, bool STAGE = false>
 struct Dopri5Stepper {
     static constexpr int N = Sys::DIM;
+    static constexpr bool kStage = STAGE;
     static constexpr bool DENSE = OUT == ODE_B200_OUT_DENSE;
     static constexpr bool CONT = OUT == ODE_B200_OUT_CONTINUOUS;
     static constexpr bool TRACK_LAST = DENSE && Sys::HAS_SOLOUT;
@@ -155,7 +157,7 @@ struct Dopri5Stepper {
         s.traj = t;
         load_traj_<Sys>(a, t, s.y, s.p);
         s.x = s.x_old = s.xd = a.cfg.x0;
-        counters_init_(s.c);
+        counters_init_<STAGE>(s.c);
         ctrl_init_(s.ctrl, a);
         s.iasti = s.non_stiff = s.stiff_ctr = 0;
         s.h = a.cfg.h0;
@@ -164,7 +166,7 @@ struct Dopri5Stepper {
             s.c.num_eval += 2;
         }
         s.h_old = s.h;
-        if constexpr (OUT == ODE_B200_OUT_SPARSE) push_<N>(a, t, s.c.out_count, s.x, s.y);
+        if constexpr (OUT == ODE_B200_OUT_SPARSE) push_<N, STAGE>(a, t, s.c, s.x, s.y);
         Sys::rhs(s.x, s.y, s.k0, s.p);
         s.c.num_eval += 1;
     }
@@ -299,7 +301,7 @@ struct Dopri5Stepper {
                     if (fabs(s.x_old) <= fabs(s.xd) && fabs(s.x) >= fabs(s.xd)) {
                         const double th = (s.xd - s.x_old) / s.h_old, th1 = 1.0 - th;
                         y_out(rc, th, th1, yo);
-                        push_<N>(a, s.traj, s.c.out_count, s.xd, yo);
+                        push_<N, STAGE>(a, s.traj, s.c, s.xd, yo);
                         if constexpr (TRACK_LAST) {
 #pragma unroll
                             for (int i = 0; i < N; ++i) s.ylast[i] = yo[i];
@@ -319,7 +321,7 @@ struct Dopri5Stepper {
                 if (fabs(s.xd - cfg.x_end) < 1.0e-9) { /* endpoint rule, dopri5.rs:472-478 (Q9) */
                     const double th = (cfg.x_end - s.x_old) / s.h_old, th1 = 1.0 - th;
                     y_out(rc, th, th1, yo);
-                    push_<N>(a, s.traj, s.c.out_count, cfg.x_end, yo);
+                    push_<N, STAGE>(a, s.traj, s.c, cfg.x_end, yo);
                     if constexpr (TRACK_LAST) {
 #pragma unroll
                         for (int i = 0; i < N; ++i) s.ylast[i] = yo[i];
@@ -329,7 +331,7 @@ struct Dopri5Stepper {
                 if (s.c.out_count == 0) return finish(s, a, ODE_B200_UNSUPPORTED_DOMAIN);
                 if constexpr (Sys::HAS_SOLOUT) stop = Sys::solout(s.x, s.ylast, s.k0, s.p);
             } else {
-                push_<N>(a, s.traj, s.c.out_count, s.x, s.y);
+                push_<N, STAGE>(a, s.traj, s.c, s.x, s.y);
                 if constexpr (CONT) { /* add_interval(|x|, rcont, h_old), dopri5.rs:484-486 */
                     const ode_b200_outputs& o = a.out;
                     if (o.com_break != nullptr && (long long)s.c.com_count < o.com_cap) {
@@ -360,9 +362,10 @@ struct Dopri5Stepper {
 
 /* ============================================================================ Dop853 */
 /* OUT: Dense, or Sparse (the reference treats Continuous like Sparse: dop853.rs:398,540-542) */
-template <class Sys, int OUT>
+template <class Sys, int OUT, bool STAGE = false>
 struct Dop853Stepper {
     static constexpr int N = Sys::DIM;
+    static constexpr bool kStage = STAGE;
     static constexpr bool DENSE = OUT == ODE_B200_OUT_DENSE;
     static constexpr bool TRACK_LAST = DENSE && Sys::HAS_SOLOUT;
     static constexpr int kMinBlocks = min_blocks_for<N, ODE_B200_DOP853, DENSE>();
@@ -400,7 +403,7 @@ struct Dop853Stepper {
         s.traj = t;
         load_traj_<Sys>(a, t, s.y, s.p);
         s.x = s.x_old = s.xd = a.cfg.x0;
-        counters_init_(s.c);
+        counters_init_<STAGE>(s.c);
         ctrl_init_(s.ctrl, a);
         s.iasti = s.non_stiff = s.stiff_ctr = 0;
         s.h = a.cfg.h0;
@@ -412,14 +415,14 @@ struct Dop853Stepper {
         /* solution_output(y0), dop853.rs:273-274 -> :515-519 / :541 */
         if constexpr (DENSE) {
             /* first call: |xd - x0| = 0 < EPSILON always */
-            push_<N>(a, t, s.c.out_count, a.cfg.x0, s.y);
+            push_<N, STAGE>(a, t, s.c, a.cfg.x0, s.y);
             if constexpr (TRACK_LAST) {
 #pragma unroll
                 for (int i = 0; i < N; ++i) s.ylast[i] = s.y[i];
             }
             s.xd += a.cfg.dx;
         } else {
-            push_<N>(a, t, s.c.out_count, a.cfg.x0, s.y);
+            push_<N, STAGE>(a, t, s.c, a.cfg.x0, s.y);
         }
         Sys::rhs(s.x, s.y, s.k0, s.p);
         s.c.num_eval += 1;
@@ -623,7 +626,7 @@ struct Dop853Stepper {
             if constexpr (DENSE) {
                 double yo[N];
                 if (fabs(s.xd - cfg.x0) < 2.220446049250313e-16) {
-                    push_<N>(a, s.traj, s.c.out_count, cfg.x0, s.y);
+                    push_<N, STAGE>(a, s.traj, s.c, cfg.x0, s.y);
                     if constexpr (TRACK_LAST) {
 #pragma unroll
                         for (int i = 0; i < N; ++i) s.ylast[i] = s.y[i];
@@ -635,7 +638,7 @@ struct Dop853Stepper {
                         if (fabs(s.x_old) <= fabs(s.xd) && fabs(s.x) >= fabs(s.xd)) {
                             const double th = (s.xd - s.x_old) / s.h_old, th1 = 1.0 - th;
                             y_out(rc, th, th1, yo);
-                            push_<N>(a, s.traj, s.c.out_count, s.xd, yo);
+                            push_<N, STAGE>(a, s.traj, s.c, s.xd, yo);
                             if constexpr (TRACK_LAST) {
 #pragma unroll
                                 for (int i = 0; i < N; ++i) s.ylast[i] = yo[i];
@@ -651,7 +654,7 @@ struct Dop853Stepper {
                     if (fabs(s.xd - cfg.x_end) < 1.0e-9) {
                         const double th = (cfg.x_end - s.x_old) / s.h_old, th1 = 1.0 - th;
                         y_out(rc, th, th1, yo);
-                        push_<N>(a, s.traj, s.c.out_count, cfg.x_end, yo);
+                        push_<N, STAGE>(a, s.traj, s.c, cfg.x_end, yo);
                         if constexpr (TRACK_LAST) {
 #pragma unroll
                             for (int i = 0; i < N; ++i) s.ylast[i] = yo[i];
@@ -660,7 +663,7 @@ struct Dop853Stepper {
                     }
                 }
             } else {
-                push_<N>(a, s.traj, s.c.out_count, cfg.x0, s.y); /* pushes x0, not x (Q6) */
+                push_<N, STAGE>(a, s.traj, s.c, cfg.x0, s.y); /* pushes x0, not x (Q6) */
             }
 
             bool stop = false;
