@@ -319,7 +319,8 @@ def run_native(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_s / args.steps, "kernel_ms_inside": e2e_kernel_ms,
-                "api": "ode_b200_integrate_batch (host pointers, pinned)"},
+                "api": "ode_b200_integrate_batch (host pointers, pinned): y0/params by cudaMemcpyAsync, per-trajectory "
+                       "results written by the kernel straight into the pinned host arrays over PCIe"},
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
         "roofline": roofline,

@@ -218,3 +218,36 @@ def test_multi_gpu_entry_with_one_gpu_matches_single():
         assert lib.ode_b200_integrate_batch_multi(f.sys_id, C.byref(cfg), 777, y0.ctypes.data, p.ctypes.data, 0, 2,
                                                   C.byref(s2)) == 0
         assert_same_outputs(a, out2, "multi(2) vs single")
+
+
+def test_pinned_host_outputs_take_the_zero_copy_path_with_identical_results():
+    """pinned (device-mapped) output arrays are written directly by the kernel; pageable ones go
+    through the staged copy: same bits either way"""
+    import ctypes as C
+    import torch
+    from ode_solvers_b200 import _abi
+    n = 5000
+    y0, p = W.lorenz_ensemble(n, offset=99)
+    cfg = ob.config_new(ob.DOPRI5, 0.0, 3.0, 0.1, 1e-6, 1e-6, out_type=ob.OUT_SPARSE)
+    f = ob.System.builtin("lorenz")
+    ref = ob.integrate_batch(f, cfg, y0, p)  # numpy (pageable) outputs
+    pin = {k: torch.zeros(n, dtype=torch.float64).pin_memory() for k in ("x_final", "h_next")}
+    pin["y_final"] = torch.zeros((3, n), dtype=torch.float64).pin_memory()
+    for k in ("num_eval", "accepted", "rejected", "n_step", "status"):
+        pin[k] = torch.full((n,), -7, dtype=torch.int32).pin_memory()
+    o = _abi.Outputs()
+    for k in ("y_final", "x_final", "h_next"):
+        setattr(o, k, C.cast(pin[k].data_ptr(), _abi.c_double_p))
+    for k in ("num_eval", "accepted", "rejected", "n_step"):
+        setattr(o, k, C.cast(pin[k].data_ptr(), _abi.c_u32_p))
+    o.status = C.cast(pin["status"].data_ptr(), _abi.c_i32_p)
+    ctx = ob.default_context(0)
+    pp = np.ascontiguousarray(p)
+    rc = _abi.load().ode_b200_integrate_batch(ctx.handle, f.sys_id, C.byref(cfg), n, y0.ctypes.data, pp.ctypes.data,
+                                             0, C.byref(o))
+    assert rc == 0
+    assert same_f64(pin["y_final"].numpy(), ref.y_final).all()
+    assert same_f64(pin["x_final"].numpy(), ref.x_final).all() and same_f64(pin["h_next"].numpy(), ref.h_next).all()
+    for k in ("num_eval", "accepted", "rejected", "n_step"):
+        assert np.array_equal(pin[k].numpy().view(np.uint32), getattr(ref, k))
+    assert np.array_equal(pin["status"].numpy(), ref.status)
