@@ -198,7 +198,7 @@ struct Dopri5Stepper {
         const double h = s.h, x = s.x;
 
         /* 6 stages, dopri5.rs:326-340. k[s] for s = 1..6; k[6] is the reference's new k[1]. */
-        double k[7][N], ynext[N], ystiff[N];
+        double k[7][N], ynext[N];
         bool bad = false;
 #pragma unroll
         for (int i = 0; i < N; ++i) k[0][i] = s.k0[i];
@@ -218,10 +218,6 @@ struct Dopri5Stepper {
             if constexpr (sg == 1) { /* only k2 meets structural zeros (a72, e2, d2): see header note */
 #pragma unroll
                 for (int i = 0; i < N; ++i) bad |= nonfinite_(k[sg][i]);
-            }
-            if constexpr (sg == 5) {
-#pragma unroll
-                for (int i = 0; i < N; ++i) ystiff[i] = ynext[i];
             }
         });
         s.c.num_eval += 6;
@@ -248,6 +244,19 @@ struct Dopri5Stepper {
             /* stiffness detection, dopri5.rs:378-402 (accepted % n_stiff == 0 kept as a counter) */
             if (++s.stiff_ctr == cfg.n_stiff) s.stiff_ctr = 0;
             if (s.stiff_ctr == 0 || s.iasti > 0) {
+                /* y_stiff = the argument of stage 6 (dopri5.rs:335-337). It is needed once per n_stiff
+                 * accepted steps, so it is rebuilt here from the still-live k1..k5 (same operations,
+                 * same order) instead of occupying N register pairs in every pass. */
+                double ystiff[N];
+#pragma unroll
+                for (int i = 0; i < N; ++i) ystiff[i] = s.y[i];
+                static_for<0, 5>([&](auto J) {
+                    constexpr int j = decltype(J)::value;
+                    if constexpr (TabDp5::a(5, j) != 0.0) {
+#pragma unroll
+                        for (int i = 0; i < N; ++i) ystiff[i] = ystiff[i] + (k[j][i] * h) * c_dp5_a[5][j];
+                    }
+                });
                 const double num = diff_dot_<N>(k[6], k[5]);
                 const double den = diff_dot_<N>(ynext, ystiff);
                 const double h_lamb = den > 0.0 ? h * sqrt(num / den) : 0.0;
