@@ -48,7 +48,14 @@ extern "C" {
 enum { ODE_B200_RK4 = 0, ODE_B200_DOPRI5 = 1, ODE_B200_DOP853 = 2 };
 
 /* OutputType, src/dop_shared.rs:112-117 (same order as the Rust enum) */
-enum { ODE_B200_OUT_DENSE = 0, ODE_B200_OUT_SPARSE = 1, ODE_B200_OUT_CONTINUOUS = 2 };
+enum { ODE_B200_OUT_DENSE = 0, ODE_B200_OUT_SPARSE = 1, ODE_B200_OUT_CONTINUOUS = 2,
+       /* EXTENSION (not in the reference, which builds a ContinuousOutputModel only for Dopri5 and
+        * treats Continuous like Sparse in Dop853, dop853.rs:398,540-542): Dop853 computes its 8
+        * dense-output vectors rcont[0..7] exactly as in Dense mode (dop853.rs:398-480) and records
+        * them per accepted step as ContinuousOutputModel intervals (m = 8), pushing (x, y) like
+        * Dopri5's Continuous mode. ContinuousOutputModel::evaluate on such an interval equals
+        * Dop853::compute_y_out (dop853.rs:546-559). Dop853 only. */
+       ODE_B200_OUT_CONTINUOUS8 = 3 };
 
 /* per-trajectory status: 0 = Ok(Stats); 1..3 = IntegrationError variants (src/dop_shared.rs:120-128) */
 enum {
@@ -107,7 +114,8 @@ typedef struct ode_b200_config {
  *   x_out()/y_out() are contiguous like the crate's Vec<T> / Vec<OVector<T,D>>:
  *     out_x[i*out_cap + s], out_y[(i*out_cap + s)*d + c]
  *     com_break[i*com_cap + s], com_step[i*com_cap + s], com_coef[((i*com_cap + s)*m + r)*d + c]
- *   with m = 5 coefficient vectors (rcont[0..4]) for Dopri5 (dopri5.rs:52,485).
+ *   with m = 5 coefficient vectors (rcont[0..4]) for Dopri5 (dopri5.rs:52,485), m = 8 for the
+ *   ODE_B200_OUT_CONTINUOUS8 extension of Dop853.
  */
 typedef struct ode_b200_outputs {
     double*   y_final;    /* [d][n]  state when the loop exits (last accepted y)                      */

@@ -2,7 +2,7 @@
 behind the API surface of the Rust crate `ode_solvers`. All numerics run in
 libode_b200.so (hand-written sm_100a CUDA); there is no CPU fallback."""
 from . import _abi, workloads  # noqa: F401
-from ._abi import (DOP853, DOPRI5, RK4, OUT_CONTINUOUS, OUT_DENSE, OUT_SPARSE,  # noqa: F401
+from ._abi import (DOP853, DOPRI5, RK4, OUT_CONTINUOUS, OUT_CONTINUOUS8, OUT_DENSE, OUT_SPARSE,  # noqa: F401
                    OK, MAX_NUM_STEP_REACHED, STEP_SIZE_UNDERFLOW, STIFFNESS_DETECTED,
                    OUTPUT_CAPACITY_EXCEEDED, UNSUPPORTED_DOMAIN)
 from .api import (Context, ContinuousOutputModel, Dop853, Dopri5, IntegrationError,  # noqa: F401

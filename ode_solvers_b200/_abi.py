@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("ODE_B200_LIB") or os.path.join(HERE, "libode_b200.so"
 
 # method ids / OutputType (src/dop_shared.rs:112-117) / status codes (src/dop_shared.rs:120-128)
 RK4, DOPRI5, DOP853 = 0, 1, 2
-OUT_DENSE, OUT_SPARSE, OUT_CONTINUOUS = 0, 1, 2
+OUT_DENSE, OUT_SPARSE, OUT_CONTINUOUS, OUT_CONTINUOUS8 = 0, 1, 2, 3
 (OK, MAX_NUM_STEP_REACHED, STEP_SIZE_UNDERFLOW, STIFFNESS_DETECTED,
  OUTPUT_CAPACITY_EXCEEDED, UNSUPPORTED_DOMAIN) = range(6)
 MAX_DIM, MAX_PARAMS = 32, 16

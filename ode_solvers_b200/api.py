@@ -444,6 +444,12 @@ class Dop853(_Stepper):
     def integrate(self, ctx=None):
         return self._run(ctx=ctx)
 
+    def integrate_with_continuous_output_model(self, continuous_output, ctx=None):
+        """EXTENSION (the reference has this for Dopri5 only): record Dop853's 8 dense-output
+        vectors per accepted step as model intervals (ODE_B200_OUT_CONTINUOUS8)."""
+        self.cfg.out_type = _abi.OUT_CONTINUOUS8
+        return self._run(com=continuous_output, ctx=ctx)
+
 
 class Rk4(_Stepper):
     """src/rk4.rs -- note the argument order (f, x, y, x_end, step_size)"""

@@ -114,7 +114,7 @@ extern "C" int ode_b200_system_compile(int sys_id, int method, int out_type) {
     SysInfo s;
     if (!sys_info(sys_id, &s)) return fail(ODE_B200_ERR_UNKNOWN_SYSTEM, "bad sys_id");
     if (method < ODE_B200_RK4 || method > ODE_B200_DOP853 || out_type < ODE_B200_OUT_DENSE ||
-        out_type > ODE_B200_OUT_CONTINUOUS)
+        out_type > ODE_B200_OUT_CONTINUOUS8 || (out_type == ODE_B200_OUT_CONTINUOUS8 && method == ODE_B200_DOPRI5))
         return fail(ODE_B200_ERR_INVALID_ARGUMENT, "system_compile: bad method / out_type");
     if (!s.jit) return ODE_B200_SUCCESS; /* built-ins are compiled ahead of time */
     std::string err;
@@ -166,7 +166,7 @@ extern "C" int ode_b200_config_from_param(int method, double x, double x_end, do
                                           double h_max, double h, uint32_t n_max, uint32_t n_stiff, int out_type,
                                           ode_b200_config* c) {
     if (!c) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "config is NULL");
-    if (out_type < ODE_B200_OUT_DENSE || out_type > ODE_B200_OUT_CONTINUOUS)
+    if (out_type < ODE_B200_OUT_DENSE || out_type > ODE_B200_OUT_CONTINUOUS8)
         return fail(ODE_B200_ERR_INVALID_ARGUMENT, "config_from_param: bad out_type");
     memset(c, 0, sizeof(*c));
     c->method = method;
@@ -308,8 +308,10 @@ static int validate(const ode_b200_config* cfg, const SysInfo& s, int64_t n, con
     if (n > 0 && s.n_params > 0 && !params) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "params is NULL");
     if (cfg->method < ODE_B200_RK4 || cfg->method > ODE_B200_DOP853)
         return fail(ODE_B200_ERR_INVALID_ARGUMENT, "bad method");
-    if (cfg->out_type < ODE_B200_OUT_DENSE || cfg->out_type > ODE_B200_OUT_CONTINUOUS)
+    if (cfg->out_type < ODE_B200_OUT_DENSE || cfg->out_type > ODE_B200_OUT_CONTINUOUS8)
         return fail(ODE_B200_ERR_INVALID_ARGUMENT, "bad out_type");
+    if (cfg->out_type == ODE_B200_OUT_CONTINUOUS8 && cfg->method == ODE_B200_DOPRI5)
+        return fail(ODE_B200_ERR_INVALID_ARGUMENT, "ODE_B200_OUT_CONTINUOUS8 is a Dop853-only extension");
     if (out->out_cap < 0 || out->com_cap < 0) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "negative capacity");
     if (out->out_cap > 0 && (!out->out_x || !out->out_y))
         return fail(ODE_B200_ERR_INVALID_ARGUMENT, "out_cap > 0 needs out_x and out_y");

@@ -1,7 +1,8 @@
 /*
  * ode_instantiate.cuh -- instantiate the step-loop kernels of one system ahead of time.
  * One translation unit per built-in system (inst_*.cu) so `make -j` compiles them in parallel.
- * Dop853 ignores OutputType::Continuous (it behaves like Sparse: dop853.rs:398,540-542).
+ * Dop853 ignores OutputType::Continuous (it behaves like Sparse: dop853.rs:398,540-542);
+ * ODE_B200_OUT_CONTINUOUS8 is this library's Dop853-only extension.
  */
 #pragma once
 
@@ -13,13 +14,14 @@
 
 #define ODE_B200_KSET(SYS, ST)                                                                              \
     {{ODE_B200_KPTR(ode_b200::Rk4Stepper<ode_b200::SYS, ST>), ODE_B200_KPTR(ode_b200::Rk4Stepper<ode_b200::SYS, ST>), \
-      ODE_B200_KPTR(ode_b200::Rk4Stepper<ode_b200::SYS, ST>)},                                               \
+      ODE_B200_KPTR(ode_b200::Rk4Stepper<ode_b200::SYS, ST>), ODE_B200_KPTR(ode_b200::Rk4Stepper<ode_b200::SYS, ST>)}, \
      {ODE_B200_KPTR(ode_b200::Dopri5Stepper<ode_b200::SYS, ODE_B200_OUT_DENSE, ST>),                         \
       ODE_B200_KPTR(ode_b200::Dopri5Stepper<ode_b200::SYS, ODE_B200_OUT_SPARSE, ST>),                        \
-      ODE_B200_KPTR(ode_b200::Dopri5Stepper<ode_b200::SYS, ODE_B200_OUT_CONTINUOUS, ST>)},                   \
+      ODE_B200_KPTR(ode_b200::Dopri5Stepper<ode_b200::SYS, ODE_B200_OUT_CONTINUOUS, ST>), nullptr},          \
      {ODE_B200_KPTR(ode_b200::Dop853Stepper<ode_b200::SYS, ODE_B200_OUT_DENSE, ST>),                         \
       ODE_B200_KPTR(ode_b200::Dop853Stepper<ode_b200::SYS, ODE_B200_OUT_SPARSE, ST>),                        \
-      ODE_B200_KPTR(ode_b200::Dop853Stepper<ode_b200::SYS, ODE_B200_OUT_SPARSE, ST>)}}
+      ODE_B200_KPTR(ode_b200::Dop853Stepper<ode_b200::SYS, ODE_B200_OUT_SPARSE, ST>),                        \
+      ODE_B200_KPTR(ode_b200::Dop853Stepper<ode_b200::SYS, ODE_B200_OUT_CONTINUOUS8, ST>)}}
 
 #define ODE_B200_DEFINE_SYSTEM(SYS, NAME)                                                \
     extern "C" const ode_b200::SystemEntry ode_b200_entry_##NAME = {                     \

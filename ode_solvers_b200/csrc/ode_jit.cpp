@@ -119,7 +119,7 @@ std::string stepper_expr(int method, int out_type, bool staged) {
     if (method == ODE_B200_DOPRI5)
         return "ode_b200::Dopri5Stepper<ode_b200::SysUser, " + std::to_string(out_type) + st;
     /* Dop853 treats Continuous like Sparse (dop853.rs:398,540-542) */
-    const int o = out_type == ODE_B200_OUT_DENSE ? ODE_B200_OUT_DENSE : ODE_B200_OUT_SPARSE;
+    const int o = out_type == ODE_B200_OUT_DENSE || out_type == ODE_B200_OUT_CONTINUOUS8 ? out_type : ODE_B200_OUT_SPARSE;
     return "ode_b200::Dop853Stepper<ode_b200::SysUser, " + std::to_string(o) + st;
 }
 
@@ -190,8 +190,8 @@ bool compile_cubin(const JitSystem& s, int method, int out_type, bool staged, Cu
 
 /* g_mu held */
 const Cubin* get_cubin(int idx, const JitSystem& s, int method, int out_type, bool staged, std::string* err) {
-    const int o = method == ODE_B200_RK4 ? 0 : (method == ODE_B200_DOP853 && out_type != ODE_B200_OUT_DENSE
-                                                    ? ODE_B200_OUT_SPARSE : out_type);
+    const int o = method == ODE_B200_RK4 ? 0
+                  : (method == ODE_B200_DOP853 && out_type == ODE_B200_OUT_CONTINUOUS ? ODE_B200_OUT_SPARSE : out_type);
     auto key = std::make_tuple(idx, method, o, staged ? 1 : 0);
     auto it = g_cubins.find(key);
     if (it != g_cubins.end()) return &it->second;

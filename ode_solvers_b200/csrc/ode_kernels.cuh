@@ -370,14 +370,16 @@ struct Dopri5Stepper {
 };
 
 /* ============================================================================ Dop853 */
-/* OUT: Dense, or Sparse (the reference treats Continuous like Sparse: dop853.rs:398,540-542) */
+/* OUT: Dense, Sparse (the reference treats Continuous like Sparse: dop853.rs:398,540-542), or the
+ * ODE_B200_OUT_CONTINUOUS8 extension (rcont[0..7] recorded as ContinuousOutputModel intervals) */
 template <class Sys, int OUT, bool STAGE = false>
 struct Dop853Stepper {
     static constexpr int N = Sys::DIM;
     static constexpr bool kStage = STAGE;
     static constexpr bool DENSE = OUT == ODE_B200_OUT_DENSE;
+    static constexpr bool CONT8 = OUT == ODE_B200_OUT_CONTINUOUS8;
     static constexpr bool TRACK_LAST = DENSE && Sys::HAS_SOLOUT;
-    static constexpr int kMinBlocks = min_blocks_for<N, ODE_B200_DOP853, DENSE>();
+    static constexpr int kMinBlocks = min_blocks_for<N, ODE_B200_DOP853, DENSE || CONT8>();
 
     struct State {
         double y[N], k0[N]; /* k0 = reference k[0] = f(x, y) */
@@ -391,7 +393,7 @@ struct Dop853Stepper {
     };
 
     ODE_DEV static bool finish(State& s, const KernelArgs& a, int status) {
-        store_final_<N>(a, s.traj, s.y, s.x, s.h_old, s.c, status, 0.0);
+        store_final_<N>(a, s.traj, s.y, s.x, s.h_old, s.c, status, CONT8 ? a.cfg.x0 : 0.0);
         return true;
     }
 
@@ -550,7 +552,7 @@ struct Dop853Stepper {
             }
 
             double rc[8][N];
-            if constexpr (DENSE) { /* dop853.rs:398-480 */
+            if constexpr (DENSE || CONT8) { /* dop853.rs:398-480 */
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
                     rc[0][i] = s.y[i];
@@ -671,6 +673,21 @@ struct Dop853Stepper {
                         s.xd += cfg.dx;
                     }
                 }
+            } else if constexpr (CONT8) {
+                /* extension: (x, y) like Dopri5's Continuous push (dopri5.rs:479-481) and
+                 * add_interval(|x|, rcont[0..7], h_old) like dopri5.rs:484-486 */
+                push_<N, STAGE>(a, s.traj, s.c, s.x, s.y);
+                const ode_b200_outputs& o = a.out;
+                if (o.com_break != nullptr && (long long)s.c.com_count < o.com_cap) {
+                    const size_t q = (size_t)s.traj * (size_t)o.com_cap + s.c.com_count;
+                    o.com_break[q] = fabs(s.x);
+                    o.com_step[q] = s.h_old;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+#pragma unroll
+                        for (int i = 0; i < N; ++i) o.com_coef[(q * 8 + r) * N + i] = rc[r][i];
+                }
+                s.c.com_count += 1;
             } else {
                 push_<N, STAGE>(a, s.traj, s.c, cfg.x0, s.y); /* pushes x0, not x (Q6) */
             }

@@ -11,8 +11,8 @@ struct SystemEntry {
     int dim;
     int n_params;
     int has_solout;
-    /* [staged results: no, yes][method: Rk4, Dopri5, Dop853][out_type: Dense, Sparse, Continuous] */
-    const void* kernels[2][3][3];
+    /* [staged results: no, yes][method: Rk4, Dopri5, Dop853][out_type: Dense, Sparse, Continuous, Continuous8] */
+    const void* kernels[2][3][4];
 };
 
 }  // namespace ode_b200

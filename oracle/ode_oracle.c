@@ -479,6 +479,8 @@ static void dp8_solution_output(dp8_state_t* st, sink_t* sink, const double* y_n
                 st->xd += st->dx;
             }
         }
+    } else if (st->out_type == ODE_B200_OUT_CONTINUOUS8) {
+        sink_push(sink, st->x, y_next); /* extension: (x, y) like Dopri5's Continuous push (dopri5.rs:479-481) */
     } else {
         sink_push(sink, st->x0, y_next); /* pushes x0, not x (Q6) */
     }
@@ -497,7 +499,9 @@ static void dop853_integrate(const ode_oracle_system* S, const ode_b200_config* 
     st.dx = cfg->dx;
     memcpy(st.y, y0, sizeof(double) * n);
     const double rtol = cfg->rtol, atol = cfg->atol, uround = cfg->uround;
-    const int dense = cfg->out_type == ODE_B200_OUT_DENSE;
+    /* ODE_B200_OUT_CONTINUOUS8 (extension, see include/ode_b200.h): Dense-mode numerics, intervals recorded */
+    const int cont8 = cfg->out_type == ODE_B200_OUT_CONTINUOUS8;
+    const int dense = cfg->out_type == ODE_B200_OUT_DENSE || cont8;
     double k[12][MAXD], y_next[MAXD], err_est[MAXD], err_bhh[MAXD], t1[MAXD], t2[MAXD];
     memset(k, 0, sizeof(k)); /* dop853.rs:276 */
     memset(y_next, 0, sizeof(y_next));
@@ -509,7 +513,7 @@ static void dop853_integrate(const ode_oracle_system* S, const ode_b200_config* 
     int last = 0;
     const double posneg = sign_(1.0, st.x_end - st.x);
     R->status = ODE_B200_OK;
-    R->com_lower = 0.0;
+    R->com_lower = cont8 ? st.x : 0.0;
 
     if (h == 0.0) {
         h = hinit(S, p, st.x, st.x_end, st.y, rtol, atol, C.h_max, 0.125);
@@ -661,6 +665,7 @@ static void dop853_integrate(const ode_oracle_system* S, const ode_b200_config* 
 
             dp8_solution_output(&st, sink, k[4]);
             if (st.bad) break;
+            if (cont8) sink_add_interval(sink, fabs(st.x), st.rc, st.h_old);
 
             if (sink->count == 0) {
                 st.bad = 1;

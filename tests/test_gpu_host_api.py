@@ -251,3 +251,27 @@ def test_pinned_host_outputs_take_the_zero_copy_path_with_identical_results():
     for k in ("num_eval", "accepted", "rejected", "n_step"):
         assert np.array_equal(pin[k].numpy().view(np.uint32), getattr(ref, k))
     assert np.array_equal(pin["status"].numpy(), ref.status)
+
+
+def test_dop853_continuous_output_model_extension():
+    """BASELINE config 4: Dop853 'with dense output into ContinuousOutputModel' -- an extension (the
+    reference builds the model for Dopri5 only). The model must reproduce Dop853's own dense samples."""
+    f = ob.System.builtin("cr3bp", [W.CR3BP_MU])
+    dense = ob.Dop853.new(f, 0.0, 5.0, 0.25, W.CR3BP_Y0, 1e-12, 1e-12)
+    st_d = dense.integrate()
+    s = ob.Dop853.new(f, 0.0, 5.0, 0.25, W.CR3BP_Y0, 1e-12, 1e-12)
+    com = ob.ContinuousOutputModel.default()
+    st_c = s.integrate_with_continuous_output_model(com)
+    assert st_c == st_d  # same numerics as Dense mode (incl. the 3 extra stages per accepted step)
+    assert len(com.intervals) == st_c.accepted_steps and len(com.intervals[0].coefficients) == 8
+    assert com.bounds() == (0.0, 5.0) and com.evaluate(-1e-3) is None and com.evaluate(5.001) is None
+    same = 0
+    for x, y in zip(dense.x_out()[1:-1], dense.y_out()[1:-1]):
+        v = com.evaluate(x)
+        assert np.allclose(v, y, rtol=1e-13, atol=1e-15)
+        same += int(np.array_equal(v, y))
+    assert same >= len(dense.x_out()) - 4
+    # Dopri5 has no such mode
+    cfg = ob.config_new(ob.DOPRI5, 0.0, 1.0, 0.1, 1e-6, 1e-6, out_type=ob.OUT_CONTINUOUS8)
+    with pytest.raises(ob.Ode200Error):
+        ob.integrate_batch(f, cfg, np.asarray(W.CR3BP_Y0).reshape(6, 1))

@@ -44,6 +44,7 @@ for sysname in ("lorenz", "kepler", "cr3bp", "robertson", "bouncing_ball", "thre
     for m in (ob.DOPRI5, ob.DOP853):
         for ot in (ob.OUT_SPARSE, ob.OUT_DENSE, ob.OUT_CONTINUOUS):
             CASES.append((sysname, m, ot))
+    CASES.append((sysname, ob.DOP853, ob.OUT_CONTINUOUS8))  # extension: Dop853 -> ContinuousOutputModel
 
 
 @pytest.mark.parametrize("system,method,out_type", CASES)
@@ -59,6 +60,8 @@ def test_bitwise_parity(system, method, out_type):
     elif system in ("kepler", "bouncing_ball", "robertson"):
         cap = 1200
     com_cap = 1200 if (out_type == ob.OUT_CONTINUOUS and method == ob.DOPRI5 and system != "lorenz") else 0
+    if out_type == ob.OUT_CONTINUOUS8:
+        cap, com_cap = 700, 700
     g, o = run_both(system, cfg, y0, p, out_cap=cap, com_cap=com_cap)
     assert (o.status != -1).all()
     assert_same_outputs(g, o, "%s m%d o%d" % (system, method, out_type))
