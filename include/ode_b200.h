@@ -223,6 +223,29 @@ int ode_b200_integrate_batch_multi(int sys_id, const ode_b200_config* cfg, int64
                                    const double* y0, const double* params, int params_per_traj,
                                    int n_gpus, const ode_b200_outputs* out);
 
+/*
+ * f32 instantiation of the fixed-step path (`impl FloatNumber for f32`, src/dop_shared.rs:74;
+ * examples/bouncing_ball.rs:15,36 runs Rk4 in f32): Rk4::new(f, x, y, x_end, step_size) and
+ * Rk4::integrate with T = f32, every operation in single precision. Available for the built-in
+ * systems whose RHS needs no libm call (lorenz, robertson, bouncing_ball, test_rk4_1, test_rk4_2).
+ * Host pointers; layouts as in ode_b200_outputs. The adaptive methods stay f64-only (their f32
+ * form needs a second libm clone, powf).
+ */
+typedef struct ode_b200_outputs_f32 {
+    float*    y_final;   /* [d][n] */
+    float*    x_final;   /* [n] */
+    uint32_t* num_eval;  /* [n] */
+    uint32_t* accepted;  /* [n] */
+    int32_t*  status;    /* [n] */
+    int64_t   out_cap;
+    float*    out_x;     /* [n][out_cap] */
+    float*    out_y;     /* [n][out_cap][d] */
+    uint32_t* out_count; /* [n] */
+} ode_b200_outputs_f32;
+int ode_b200_rk4_f32_integrate_batch(ode_b200_ctx* ctx, int sys_id, float x, float x_end, float step_size,
+                                     int64_t n_traj, const float* y0, const float* params,
+                                     int params_per_traj, const ode_b200_outputs_f32* out);
+
 /* kernel scheduling knob: 1 (default) = persistent kernel with lane refill from a work
  * queue; 0 = static one-thread-per-trajectory launch (kept for the ablation in DESIGN.md) */
 int ode_b200_set_work_queue(ode_b200_ctx* ctx, int enabled);

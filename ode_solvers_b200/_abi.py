@@ -55,6 +55,46 @@ class Outputs(C.Structure):
     ]
 
 
+c_float_p = C.POINTER(C.c_float)
+
+
+class OutputsF32(C.Structure):
+    """ode_b200_outputs_f32."""
+    _fields_ = [
+        ("y_final", c_float_p), ("x_final", c_float_p), ("num_eval", c_u32_p), ("accepted", c_u32_p),
+        ("status", c_i32_p), ("out_cap", C.c_int64), ("out_x", c_float_p), ("out_y", c_float_p),
+        ("out_count", c_u32_p),
+    ]
+
+
+class HostOutputsF32:
+    """numpy-backed ode_b200_outputs_f32."""
+
+    def __init__(self, n, dim, out_cap=0):
+        self.n, self.dim, self.out_cap = n, dim, int(out_cap)
+        self.y_final = np.zeros((dim, n), dtype=np.float32)
+        self.x_final = np.zeros(n, dtype=np.float32)
+        self.num_eval = np.zeros(n, dtype=np.uint32)
+        self.accepted = np.zeros(n, dtype=np.uint32)
+        self.status = np.full(n, -1, dtype=np.int32)
+        self.out_count = np.zeros(n, dtype=np.uint32)
+        self.out_x = np.zeros((n, out_cap), dtype=np.float32) if out_cap else None
+        self.out_y = np.zeros((n, out_cap, dim), dtype=np.float32) if out_cap else None
+
+    def struct(self):
+        o = OutputsF32()
+        o.y_final = _ptr(self.y_final, c_float_p)
+        o.x_final = _ptr(self.x_final, c_float_p)
+        o.num_eval = _ptr(self.num_eval, c_u32_p)
+        o.accepted = _ptr(self.accepted, c_u32_p)
+        o.status = _ptr(self.status, c_i32_p)
+        o.out_cap = self.out_cap
+        o.out_x = _ptr(self.out_x, c_float_p)
+        o.out_y = _ptr(self.out_y, c_float_p)
+        o.out_count = _ptr(self.out_count, c_u32_p)
+        return o
+
+
 def _ptr(a, typ):
     return a.ctypes.data_as(typ) if a is not None else typ()
 
@@ -118,6 +158,7 @@ ABI_SYMBOLS = [
     "ode_b200_create", "ode_b200_destroy", "ode_b200_last_kernel_ms", "ode_b200_launch_count",
     "ode_b200_stream",
     "ode_b200_integrate_batch", "ode_b200_integrate_batch_device", "ode_b200_integrate_batch_multi",
+    "ode_b200_rk4_f32_integrate_batch",
     "ode_b200_set_work_queue", "ode_b200_com_evaluate",
     "ode_b200_tableau", "ode_b200_debug_pow", "ode_b200_debug_exp", "ode_b200_debug_div",
 ]
@@ -185,6 +226,9 @@ def load():
     lib.ode_b200_integrate_batch_multi.argtypes = [C.c_int, C.POINTER(Config), C.c_int64, C.c_void_p,
                                                    C.c_void_p, C.c_int, C.c_int, C.POINTER(Outputs)]
     lib.ode_b200_integrate_batch_multi.restype = C.c_int
+    lib.ode_b200_rk4_f32_integrate_batch.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int64,
+                                                     C.c_void_p, C.c_void_p, C.c_int, C.POINTER(OutputsF32)]
+    lib.ode_b200_rk4_f32_integrate_batch.restype = C.c_int
     lib.ode_b200_set_work_queue.argtypes = [C.c_void_p, C.c_int]
     lib.ode_b200_set_work_queue.restype = C.c_int
     lib.ode_b200_com_evaluate.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int64,

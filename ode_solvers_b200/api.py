@@ -242,6 +242,28 @@ def integrate_batch(system, cfg, y0, params=None, out_cap=0, com_cap=0, ctx=None
     return out
 
 
+def rk4_f32_integrate_batch(system, x, x_end, step_size, y0, params=None, out_cap=0, ctx=None):
+    """Rk4 with T = f32 (src/rk4.rs over FloatNumber for f32, src/dop_shared.rs:74) for a batch.
+    y0: [dim, n] float32. Returns an _abi.HostOutputsF32."""
+    lib = _abi.load()
+    ctx = ctx or default_context(0)
+    y0 = np.ascontiguousarray(np.asarray(y0, dtype=np.float32).reshape(system.dim, -1))
+    n = y0.shape[1]
+    if params is None:
+        params = system.params
+    per_traj, pp = 0, None
+    if system.n_params:
+        params = np.ascontiguousarray(np.asarray(params, dtype=np.float32))
+        per_traj = int(params.ndim == 2)
+        pp = params.ctypes.data
+    out = _abi.HostOutputsF32(n, system.dim, out_cap)
+    s = out.struct()
+    _check(lib.ode_b200_rk4_f32_integrate_batch(ctx.handle, system.sys_id, x, x_end, step_size, n, y0.ctypes.data, pp,
+                                                per_traj, C.byref(s)), "rk4_f32_integrate_batch")
+    out.kernel_ms = ctx.last_kernel_ms
+    return out
+
+
 def com_evaluate_batch(out, xq, ctx=None):
     """Batched ContinuousOutputModel::evaluate on the device for every trajectory of `out`.
     Returns (y [n, nq, dim], found [n, nq] bool)."""

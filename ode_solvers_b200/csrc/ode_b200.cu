@@ -584,6 +584,88 @@ extern "C" int ode_b200_integrate_batch(ode_b200_ctx* c, int sys_id, const ode_b
     return integrate_range(c, sys_id, cfg, n, 0, n, y0, params, per_traj, out);
 }
 
+/* Rk4 with T = f32 (see include/ode_b200.h) */
+extern "C" int ode_b200_rk4_f32_integrate_batch(ode_b200_ctx* c, int sys_id, float x, float x_end, float step_size,
+                                                int64_t n, const float* y0, const float* params, int per_traj,
+                                                const ode_b200_outputs_f32* out) {
+    if (!c) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    if (sys_id < 0 || sys_id >= kNumBuiltins) return fail(ODE_B200_ERR_UNKNOWN_SYSTEM, "f32 needs a built-in system");
+    const SystemEntry* e = kBuiltins[sys_id];
+    if (!e->rk4_f32_kernel)
+        return fail(ODE_B200_ERR_UNKNOWN_SYSTEM, std::string("system '") + e->name + "' has no f32 instantiation");
+    if (!out || n < 0 || (n > 0 && !y0) || (n > 0 && e->n_params > 0 && !params) || out->out_cap < 0 ||
+        (out->out_cap > 0 && (!out->out_x || !out->out_y)))
+        return fail(ODE_B200_ERR_INVALID_ARGUMENT, "rk4_f32: bad arguments");
+    if (n == 0) return ODE_B200_SUCCESS;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t d = (size_t)e->dim, np = (size_t)e->n_params;
+    if (ensure(c, c->y0, d * n * 4)) return ODE_B200_ERR_CUDA;
+    CUDA_TRY(cudaMemcpyAsync(c->y0.p, y0, d * n * 4, cudaMemcpyHostToDevice, st));
+    if (np) {
+        const size_t pb = (per_traj ? np * n : np) * 4;
+        if (ensure(c, c->params, pb)) return ODE_B200_ERR_CUDA;
+        CUDA_TRY(cudaMemcpyAsync(c->params.p, params, pb, cudaMemcpyHostToDevice, st));
+    }
+    KernelArgsF32 ka;
+    memset(&ka, 0, sizeof(ka));
+    ka.x0 = x;
+    ka.x_end = x_end;
+    ka.step_size = step_size;
+    ka.n_traj = n;
+    ka.y0 = (const float*)c->y0.p;
+    ka.params = (const float*)c->params.p;
+    ka.params_per_traj = per_traj ? 1 : 0;
+    ka.use_queue = c->use_queue;
+    ka.queue = c->queue;
+    ode_b200_outputs_f32& dv = ka.out;
+#define WANT32(field, buf, bytes)                                 \
+    if (out->field) {                                             \
+        if (ensure(c, c->buf, (bytes))) return ODE_B200_ERR_CUDA; \
+        dv.field = (decltype(dv.field))c->buf.p;                  \
+    }
+    WANT32(y_final, y_final, d * n * 4)
+    WANT32(x_final, x_final, n * 4)
+    WANT32(num_eval, num_eval, n * 4)
+    WANT32(accepted, accepted, n * 4)
+    WANT32(status, status, n * 4)
+    WANT32(out_count, out_count, n * 4)
+    if (out->out_cap > 0) {
+        dv.out_cap = out->out_cap;
+        WANT32(out_x, out_x, (size_t)n * out->out_cap * 4)
+        WANT32(out_y, out_y, (size_t)n * out->out_cap * d * 4)
+    }
+#undef WANT32
+    const int block = kBlockThreads;
+    const long long blocks_all = (n + block - 1) / block;
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, e->rk4_f32_kernel, block, 0));
+    long long grid = blocks_all;
+    if (c->use_queue) grid = std::min<long long>(blocks_all, (long long)c->num_sms * std::max(per_sm, 1));
+    CUDA_TRY(cudaMemsetAsync(c->queue, 0, sizeof(unsigned long long), st));
+    CUDA_TRY(cudaEventRecord(c->ev0, st));
+    void* args[] = {&ka};
+    CUDA_TRY(cudaLaunchKernel(e->rk4_f32_kernel, dim3((unsigned)grid), dim3(block), args, 0, st));
+    CUDA_TRY(cudaEventRecord(c->ev1, st));
+    c->timed = true;
+    c->launches++;
+#define BACK32(field, bytes) \
+    if (out->field) CUDA_TRY(cudaMemcpyAsync(out->field, dv.field, (bytes), cudaMemcpyDeviceToHost, st));
+    BACK32(y_final, d * n * 4)
+    BACK32(x_final, n * 4)
+    BACK32(num_eval, n * 4)
+    BACK32(accepted, n * 4)
+    BACK32(status, n * 4)
+    BACK32(out_count, n * 4)
+    if (out->out_cap > 0) {
+        BACK32(out_x, (size_t)n * out->out_cap * 4)
+        BACK32(out_y, (size_t)n * out->out_cap * d * 4)
+    }
+#undef BACK32
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return ODE_B200_SUCCESS;
+}
+
 /* contiguous index ranges, one host thread + context + stream per GPU, no collective */
 extern "C" int ode_b200_integrate_batch_multi(int sys_id, const ode_b200_config* cfg, int64_t n,
                                               const double* y0, const double* params, int per_traj, int n_gpus,

@@ -10,6 +10,16 @@
 #include "ode_registry.h"
 #include "ode_systems.cuh"
 
+namespace ode_b200 {
+template <class Sys>
+const void* rk4_f32_kernel_ptr() {
+    if constexpr (Sys::HAS_F32)
+        return (const void*)&ode_rk4_f32_kernel<Sys>;
+    else
+        return nullptr;
+}
+}  // namespace ode_b200
+
 #define ODE_B200_KPTR(...) ((const void*)&ode_b200::ode_step_loop_kernel<__VA_ARGS__>)
 
 #define ODE_B200_KSET(SYS, ST)                                                                              \
@@ -26,4 +36,4 @@
 #define ODE_B200_DEFINE_SYSTEM(SYS, NAME)                                                \
     extern "C" const ode_b200::SystemEntry ode_b200_entry_##NAME = {                     \
         #NAME, ode_b200::SYS::DIM, ode_b200::SYS::NP, ode_b200::SYS::HAS_SOLOUT ? 1 : 0, \
-        {ODE_B200_KSET(SYS, false), ODE_B200_KSET(SYS, true)}};
+        {ODE_B200_KSET(SYS, false), ODE_B200_KSET(SYS, true)}, ode_b200::rk4_f32_kernel_ptr<ode_b200::SYS>()};

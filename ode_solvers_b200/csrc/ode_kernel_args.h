@@ -47,4 +47,16 @@ struct KernelArgs {
     ode_b200_outputs out;       /* device pointers */
 };
 
+/* the f32 Rk4 kernel's arguments (device pointers) */
+struct KernelArgsF32 {
+    float x0, x_end, step_size;
+    long long n_traj;
+    const float* y0;
+    const float* params;
+    int params_per_traj;
+    int use_queue;
+    unsigned long long* queue;
+    ode_b200_outputs_f32 out;
+};
+
 }  // namespace ode_b200

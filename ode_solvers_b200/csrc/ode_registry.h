@@ -13,6 +13,8 @@ struct SystemEntry {
     int has_solout;
     /* [staged results: no, yes][method: Rk4, Dopri5, Dop853][out_type: Dense, Sparse, Continuous, Continuous8] */
     const void* kernels[2][3][4];
+    /* Rk4 with T = f32 (nullptr when the system's RHS is f64-only) */
+    const void* rk4_f32_kernel;
 };
 
 }  // namespace ode_b200

@@ -9,6 +9,9 @@
  * operation order (powi(2) = v*v, powi(3) = (v*v)*v, left-associated sums), so that with
  * -fmad=false the device produces the bits the crate produces on the host.
  * rhs must write every component of dy.
+ *
+ * Systems whose rhs is a template on the scalar type T (HAS_F32) also instantiate for f32, the
+ * reference's other FloatNumber (src/dop_shared.rs:74; examples/bouncing_ball.rs:15 runs in f32).
  */
 #pragma once
 
@@ -19,19 +22,21 @@ namespace ode_b200 {
 /* examples/lorenz.rs:42-54 ; p = {sigma, beta, rho} */
 struct SysLorenz {
     static constexpr int DIM = 3, NP = 3;
-    static constexpr bool HAS_SOLOUT = false;
-    ODE_DEV static void rhs(double, const double* y, double* dy, const double* p) {
+    static constexpr bool HAS_SOLOUT = false, HAS_F32 = true;
+    template <class T>
+    ODE_DEV static void rhs(T, const T* y, T* dy, const T* p) {
         dy[0] = p[0] * (y[1] - y[0]);
         dy[1] = y[0] * (p[2] - y[2]) - y[1];
         dy[2] = y[0] * y[1] - p[1] * y[2];
     }
-    ODE_DEV static bool solout(double, const double*, const double*, const double*) { return false; }
+    template <class T>
+    ODE_DEV static bool solout(T, const T*, const T*, const T*) { return false; }
 };
 
 /* examples/kepler_orbit.rs:51-66 ; p = {mu} */
 struct SysKepler {
     static constexpr int DIM = 6, NP = 1;
-    static constexpr bool HAS_SOLOUT = false;
+    static constexpr bool HAS_SOLOUT = false, HAS_F32 = false;
     ODE_DEV static void rhs(double, const double* y, double* dy, const double* p) {
         const double r = sqrt(y[0] * y[0] + y[1] * y[1] + y[2] * y[2]);
         const double r3 = r * r * r;
@@ -51,7 +56,7 @@ struct SysKepler {
 /* examples/three_body_system.rs:40-59 (circular restricted three-body problem) ; p = {mu} */
 struct SysCr3bp {
     static constexpr int DIM = 6, NP = 1;
-    static constexpr bool HAS_SOLOUT = false;
+    static constexpr bool HAS_SOLOUT = false, HAS_F32 = false;
     ODE_DEV static void rhs(double, const double* y, double* dy, const double* p) {
         const double mu = p[0];
         const double a = y[0] + mu, b = y[0] - 1.0 + mu;
@@ -72,32 +77,36 @@ struct SysCr3bp {
  * p = {k1, k2, k3}; p = (0.04, 1e4, 3e7) is bitwise the example */
 struct SysRobertson {
     static constexpr int DIM = 3, NP = 3;
-    static constexpr bool HAS_SOLOUT = false;
-    ODE_DEV static void rhs(double, const double* y, double* dy, const double* p) {
+    static constexpr bool HAS_SOLOUT = false, HAS_F32 = true;
+    template <class T>
+    ODE_DEV static void rhs(T, const T* y, T* dy, const T* p) {
         dy[0] = -p[0] * y[0] + p[1] * y[1] * y[2];
         dy[1] = p[0] * y[0] - p[1] * y[1] * y[2] - p[2] * y[1] * y[1];
         dy[2] = p[2] * y[1] * y[1];
     }
-    ODE_DEV static bool solout(double, const double*, const double*, const double*) { return false; }
+    template <class T>
+    ODE_DEV static bool solout(T, const T*, const T*, const T*) { return false; }
 };
 
 /* examples/bouncing_ball.rs:74-86 in f64 ; p = {g}. dy[2] = 0 written explicitly (Q13). */
 struct SysBouncingBall {
     static constexpr int DIM = 3, NP = 1;
-    static constexpr bool HAS_SOLOUT = true;
-    ODE_DEV static void rhs(double, const double* y, double* dy, const double* p) {
+    static constexpr bool HAS_SOLOUT = true, HAS_F32 = true;
+    template <class T>
+    ODE_DEV static void rhs(T, const T* y, T* dy, const T* p) {
         dy[0] = y[1];
         dy[1] = -p[0];
-        dy[2] = 0.0;
+        dy[2] = T(0);
     }
-    ODE_DEV static bool solout(double, const double* y, const double*, const double*) { return y[0] < 0.0; }
+    template <class T>
+    ODE_DEV static bool solout(T, const T* y, const T*, const T*) { return y[0] < T(0); }
 };
 
 /* Newtonian three-body problem, 18 states (not in the reference; order defined by the oracle,
  * oracle/ode_oracle_systems.c threebody18_rhs) ; p = {G*m1, G*m2, G*m3} */
 struct SysThreeBody18 {
     static constexpr int DIM = 18, NP = 3;
-    static constexpr bool HAS_SOLOUT = false;
+    static constexpr bool HAS_SOLOUT = false, HAS_F32 = false;
     ODE_DEV static void rhs(double, const double* y, double* dy, const double* p) {
 #pragma unroll
         for (int c = 0; c < 9; ++c) dy[c] = y[9 + c];
@@ -127,23 +136,27 @@ struct SysThreeBody18 {
 /* src/rk4.rs:178-186 Test1 */
 struct SysTestRk4_1 {
     static constexpr int DIM = 1, NP = 0;
-    static constexpr bool HAS_SOLOUT = false;
-    ODE_DEV static void rhs(double x, const double* y, double* dy, const double*) { dy[0] = (x - y[0]) / 2.0; }
-    ODE_DEV static bool solout(double, const double*, const double*, const double*) { return false; }
+    static constexpr bool HAS_SOLOUT = false, HAS_F32 = true;
+    template <class T>
+    ODE_DEV static void rhs(T x, const T* y, T* dy, const T*) { dy[0] = (x - y[0]) / T(2); }
+    template <class T>
+    ODE_DEV static bool solout(T, const T*, const T*, const T*) { return false; }
 };
 
 /* src/rk4.rs:188-196 Test2 */
 struct SysTestRk4_2 {
     static constexpr int DIM = 1, NP = 0;
-    static constexpr bool HAS_SOLOUT = false;
-    ODE_DEV static void rhs(double x, const double* y, double* dy, const double*) { dy[0] = -2.0 * x - y[0]; }
-    ODE_DEV static bool solout(double, const double*, const double*, const double*) { return false; }
+    static constexpr bool HAS_SOLOUT = false, HAS_F32 = true;
+    template <class T>
+    ODE_DEV static void rhs(T x, const T* y, T* dy, const T*) { dy[0] = T(-2) * x - y[0]; }
+    template <class T>
+    ODE_DEV static bool solout(T, const T*, const T*, const T*) { return false; }
 };
 
 /* src/rk4.rs:198-206 Test3 (= dopri5.rs:531-538, dop853.rs:595-602): uses f64::exp -> exp_d */
 struct SysTestExp {
     static constexpr int DIM = 1, NP = 0;
-    static constexpr bool HAS_SOLOUT = false;
+    static constexpr bool HAS_SOLOUT = false, HAS_F32 = false;
     ODE_DEV static void rhs(double x, const double* y, double* dy, const double*) {
         dy[0] = (5.0 * x * x - y[0]) / exp_d(x + y[0]);
     }
@@ -153,7 +166,7 @@ struct SysTestExp {
 /* the same with `solout: x >= 0.5` (rk4.rs:219-221, dopri5.rs:540-542, dop853.rs:604-606) ; p = {x_stop} */
 struct SysTestExpStop {
     static constexpr int DIM = 1, NP = 1;
-    static constexpr bool HAS_SOLOUT = true;
+    static constexpr bool HAS_SOLOUT = true, HAS_F32 = false;
     ODE_DEV static void rhs(double x, const double* y, double* dy, const double*) {
         dy[0] = (5.0 * x * x - y[0]) / exp_d(x + y[0]);
     }
@@ -163,7 +176,7 @@ struct SysTestExpStop {
 /* tests/dopri5.rs:13-19 : y' = -3 t^2 e^y */
 struct SysTestCubic {
     static constexpr int DIM = 1, NP = 0;
-    static constexpr bool HAS_SOLOUT = false;
+    static constexpr bool HAS_SOLOUT = false, HAS_F32 = false;
     ODE_DEV static void rhs(double x, const double* y, double* dy, const double*) {
         dy[0] = -3.0 * x * x * exp_d(y[0]);
     }
@@ -173,7 +186,7 @@ struct SysTestCubic {
 /* tests/dopri5.rs:21-31 with `solout: x >= 4.1` ; p = {x_stop} */
 struct SysTestCubicStop {
     static constexpr int DIM = 1, NP = 1;
-    static constexpr bool HAS_SOLOUT = true;
+    static constexpr bool HAS_SOLOUT = true, HAS_F32 = false;
     ODE_DEV static void rhs(double x, const double* y, double* dy, const double*) {
         dy[0] = -3.0 * x * x * exp_d(y[0]);
     }

@@ -62,6 +62,12 @@ int ode_oracle_integrate_batch(const char* system, const ode_b200_config* cfg, i
                                const double* y0, const double* params, int params_per_traj,
                                const ode_b200_outputs* out, int n_threads);
 
+/* Rk4 with T = f32 (src/rk4.rs generic over FloatNumber, src/dop_shared.rs:74), for the systems
+ * whose RHS has an f32 form. Same arguments as ode_b200_rk4_f32_integrate_batch. */
+int ode_oracle_rk4_f32_integrate_batch(const char* system, float x, float x_end, float step_size, int64_t n_traj,
+                                       const float* y0, const float* params, int params_per_traj,
+                                       const ode_b200_outputs_f32* out, int n_threads);
+
 /* ContinuousOutputModel::evaluate (src/continuous_output_model.rs:31-56,86-104) for one model.
  * Returns 1 and fills y[dim] if Some, 0 if None. */
 int ode_oracle_com_evaluate(int dim, int m, uint32_t n_intervals, double lower_bound,

@@ -111,6 +111,25 @@ def integrate_batch(system, cfg, y0, params=None, out_cap=0, com_cap=0, n_thread
     return out
 
 
+def rk4_f32_integrate_batch(system, x, x_end, step, y0, params=None, out_cap=0):
+    dim, n_params = system_info(system)
+    y0 = np.ascontiguousarray(np.asarray(y0, dtype=np.float32).reshape(dim, -1))
+    n = y0.shape[1]
+    per_traj, pp = 0, None
+    if n_params:
+        params = np.ascontiguousarray(np.asarray(params, dtype=np.float32))
+        per_traj = int(params.ndim == 2)
+        pp = params.ctypes.data
+    out = _abi.HostOutputsF32(n, dim, out_cap)
+    s = out.struct()
+    f = lib().ode_oracle_rk4_f32_integrate_batch
+    f.argtypes = [C.c_char_p, C.c_float, C.c_float, C.c_float, C.c_int64, C.c_void_p, C.c_void_p, C.c_int,
+                  C.POINTER(_abi.OutputsF32), C.c_int]
+    f.restype = C.c_int
+    assert f(system.encode(), x, x_end, step, n, y0.ctypes.data, pp, per_traj, C.byref(s), 0) == 0
+    return out
+
+
 def com_evaluate(out, i, x):
     """ContinuousOutputModel::evaluate for trajectory i of a batch result; None or ndarray."""
     cnt = int(min(out.com_count[i], out.com_cap))

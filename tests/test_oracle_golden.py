@@ -238,3 +238,14 @@ def test_error_statuses():
     cfg.n_stiff = 0
     o = _one("robertson", cfg, [1.0, 0.0, 0.0], [0.04, 1.0e4, 3.0e7], cap=0)
     assert o.status[0] == A.UNSUPPORTED_DOMAIN
+
+
+# ---------------------------------------------------------------- T = f32 (src/dop_shared.rs:74)
+def test_rk4_f32_sanity():
+    """the reference has no f32 test; the f32 oracle must still satisfy the Rk4 goldens to their 1e-5
+    tolerance and reproduce the f32 bouncing-ball example's step count (examples/bouncing_ball.rs)"""
+    o = oracle.rk4_f32_integrate_batch("test_rk4_1", 0.0, 0.2, 0.1, [1.0], out_cap=8)
+    assert abs(o.out_y[0, 1, 0] - 0.95369) < 1e-5 and abs(o.out_y[0, 2, 0] - 0.91451) < 1e-5
+    o = oracle.rk4_f32_integrate_batch("bouncing_ball", 0.0, 10.0, 0.01, [10.0, 0.0, 0.0], [9.81], out_cap=1100)
+    assert o.accepted[0] == 143 and o.out_count[0] == 144 and o.y_final[0, 0] < 0.0
+    assert o.x_final.dtype == np.float32 and abs(float(o.x_final[0]) - 1.43) < 1e-5
