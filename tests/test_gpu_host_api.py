@@ -144,6 +144,23 @@ def test_user_system_from_source_matches_builtin_bitwise():
         assert_same_outputs(a, b, "jit vs builtin m%d" % cfg.method)
 
 
+def test_user_system_recording_every_step_uses_the_staged_kernels():
+    """Sparse / Rk4 recording goes through the STAGE kernel variants (shared-memory runs); the NVRTC
+    build of those must match the ahead-of-time one bit for bit"""
+    f = ob.System.from_source(
+        "user_lorenz_staged", 3, 3,
+        "dy[0] = p[0] * (y[1] - y[0]);\n dy[1] = y[0] * (p[2] - y[2]) - y[1];\n dy[2] = y[0] * y[1] - p[1] * y[2];")
+    y0, p = W.lorenz_ensemble(200, offset=4)
+    for cfg, cap in ((ob.config_new(ob.DOPRI5, 0.0, 2.0, 0.1, 1e-6, 1e-6, out_type=ob.OUT_SPARSE), 200),
+                     (ob.config_new(ob.DOP853, 0.0, 2.0, 0.1, 1e-6, 1e-6, out_type=ob.OUT_CONTINUOUS8), 120),
+                     (ob.config_rk4(0.0, 0.3, 1e-3), 310)):
+        a = ob.integrate_batch(f, cfg, y0, p, out_cap=cap, com_cap=cap if cfg.out_type == ob.OUT_CONTINUOUS8 else 0)
+        b = ob.integrate_batch(ob.System.builtin("lorenz"), cfg, y0, p, out_cap=cap,
+                               com_cap=cap if cfg.out_type == ob.OUT_CONTINUOUS8 else 0)
+        assert_same_outputs(a, b, "jit staged m%d" % cfg.method)
+        assert (a.out_count > 10).all()
+
+
 def test_user_system_with_solout_and_exp():
     f = ob.System.from_source("user_exp_stop", 1, 1, "dy[0] = (5.0 * x * x - y[0]) / exp_d(x + y[0]);",
                               "return x >= p[0];")
