@@ -374,7 +374,7 @@ static int launch_device(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg
     if (ka.out.out_cap == 0) ka.out.out_x = ka.out.out_y = nullptr;
     if (ka.out.com_cap == 0) ka.out.com_break = ka.out.com_step = ka.out.com_coef = nullptr;
 
-    const int block = kBlockThreads;
+    const int block = block_threads_for(s.dim, cfg->method);
     const long long blocks_all = (n + block - 1) / block;
 
     /* `accepted % n_stiff` panics in the reference when n_stiff == 0 */
@@ -395,7 +395,7 @@ static int launch_device(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg
         const double samples = cfg->dx > 0.0 ? fabs(cfg->x_end - cfg->x0) / cfg->dx : 0.0;
         stage = samples >= 1000.0;
     }
-    const size_t dyn_smem = stage ? (size_t)stage_smem_doubles(s.dim) * sizeof(double) : 0;
+    const size_t dyn_smem = stage ? (size_t)stage_smem_doubles(s.dim, block) * sizeof(double) : 0;
     CUDA_TRY(cudaMemsetAsync(c->queue, 0, sizeof(unsigned long long), stream));
     if (stream == c->stream) CUDA_TRY(cudaEventRecord(c->ev0, stream));
     if (!s.jit) {
@@ -636,7 +636,7 @@ extern "C" int ode_b200_rk4_f32_integrate_batch(ode_b200_ctx* c, int sys_id, flo
         WANT32(out_y, out_y, (size_t)n * out->out_cap * d * 4)
     }
 #undef WANT32
-    const int block = kBlockThreads;
+    const int block = 128; /* __launch_bounds__ of ode_rk4_f32_kernel */
     const long long blocks_all = (n + block - 1) / block;
     int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, e->rk4_f32_kernel, block, 0));

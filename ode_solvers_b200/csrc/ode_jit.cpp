@@ -127,8 +127,14 @@ std::string make_source(const JitSystem& s, const std::string& stepper) {
     std::string src = "#include \"ode_kernels.cuh\"\nnamespace ode_b200 {\nstruct SysUser {\n";
     src += "  static constexpr int DIM = " + std::to_string(s.dim) + ", NP = " + std::to_string(s.n_params) + ";\n";
     src += std::string("  static constexpr bool HAS_SOLOUT = ") + (s.has_solout ? "true" : "false") + ";\n";
-    src += "  ODE_DEV static void rhs(double x, const double* y, double* dy, const double* p) {\n" + s.rhs_body +
-           "\n  }\n";
+    /* div_d / sqrt_d: division and square root through the kernel's math policy (ode_device.cuh,
+     * MathFast): same IEEE results as `/` and sqrt(), but branch-free inside the step loop */
+    const bool spec = s.rhs_body.find("div_d(") != std::string::npos || s.rhs_body.find("sqrt_d(") != std::string::npos;
+    src += std::string("  static constexpr bool SPEC = ") + (spec ? "true" : "false") + ";\n";
+    src += "#define div_d(a, b) ode_m_.div((a), (b))\n#define sqrt_d(v) ode_m_.sqrt(v)\n";
+    src += "  template <class M>\n  ODE_DEV static void rhs(double x, const double* y, double* dy, const double* p, M& ode_m_) {\n" +
+           s.rhs_body + "\n  }\n";
+    src += "#undef div_d\n#undef sqrt_d\n";
     src += "  ODE_DEV static bool solout(double x, const double* y, const double* dy, const double* p) {\n" +
            (s.has_solout ? s.solout_body : std::string("return false;")) + "\n  }\n};\n}\n";
     src += "template __global__ void ode_b200::ode_step_loop_kernel<" + stepper +

@@ -7,8 +7,21 @@
 
 namespace ode_b200 {
 
-/* threads per CTA of every step-loop kernel (4 warps; the persistent grid is SMs x resident CTAs) */
-constexpr int kBlockThreads = 128;
+/* Threads per CTA of a step-loop kernel (the persistent grid is SMs x resident CTAs). Small
+ * states run 4-warp CTAs, several per SM. Steppers whose unrolled per-pass code exceeds the SM's
+ * instruction cache (Dop853 with n >= 6, everything with n > 8) run ONE 8-warp CTA per SM with all
+ * 255 registers per thread and CTA-lockstep passes (run_lanes_, ode_device.cuh). Measured on B200:
+ * CR3BP/Dop853/Dense 50.7 ms (4 x 128 threads) -> 38.4 (1 x 256) -> 33.5 (lockstep);
+ * 3-body-18/Dop853 22.5 -> 16.8 -> 12.5. -DODE_B200_LOCKSTEP=0/1 forces it for measurements. */
+__host__ __device__ constexpr bool lockstep_for(int dim, int method) {
+#ifdef ODE_B200_LOCKSTEP
+    return ODE_B200_LOCKSTEP != 0 && (dim > 8 || (dim >= 6 && method == ODE_B200_DOP853));
+#else
+    return dim > 8 || (dim >= 6 && method == ODE_B200_DOP853);
+#endif
+}
+__host__ __device__ constexpr int block_threads_for(int dim, int method) { return lockstep_for(dim, method) ? 256 : 128; }
+constexpr int kMaxBlockThreads = 256;
 
 /*
  * Output staging. The per-step results are trajectory-major (one trajectory's samples are
@@ -25,7 +38,7 @@ __host__ __device__ constexpr int stage_samples(int dim) {
 }
 __host__ __device__ constexpr int stage_stride(int dim) { return (stage_samples(dim) * (1 + dim)) | 1; }
 /* dynamic shared memory of a staging launch: per-thread {staged, base} + the lane buffers */
-__host__ __device__ constexpr int stage_smem_doubles(int dim) { return kBlockThreads * (1 + stage_stride(dim)); }
+__host__ __device__ constexpr int stage_smem_doubles(int dim, int threads) { return threads * (1 + stage_stride(dim)); }
 
 struct KernelArgs {
     ode_b200_config cfg;        /* batch-uniform solver parameters (from_param argument list) */

@@ -40,11 +40,39 @@ namespace ode_b200 {
  *   CR3BP Dop853 Dense (2^18) 63.3 / 58.6 / 55.4 / 69.5 / 102.2      3-body-18 Dop853 (2^18) 18.9 / 18.0 / 18.1 / - / 26.1
  * -DODE_B200_MIN_BLOCKS=k overrides the table for such sweeps.
  */
+/*
+ * Whether a stepper's per-attempt block runs through MathFast (straight-line, checked once, exact
+ * redo out of line) or through the plain IEEE operators (MathExact inline: one branch per division
+ * and root). Systems declare SPEC = true when their right-hand side divides or takes roots through
+ * the math policy; for those the straight-line block is what lets the stage chains overlap. Dop853's
+ * error norm (2n quotients by n shared reciprocals) gains from it for every system; Dopri5 with a
+ * division-free right-hand side does not (measured on B200, 2^20 trajectories, kernel ms plain ->
+ * MathFast: Lorenz/Dop853 22.3 -> 21.0, Robertson/Dop853 11.2 -> 10.3, Lorenz/Dopri5 28.0 -> 29.0).
+ * -DODE_B200_SPEC=0/1 forces it for measurements.
+ */
+template <class Sys, int METHOD>
+constexpr bool spec_math_for() {
+#ifdef ODE_B200_SPEC
+    return ODE_B200_SPEC != 0;
+#else
+    return Sys::SPEC || METHOD == ODE_B200_DOP853;
+#endif
+}
+
+/* idle lane-passes that trigger a refill (run_lanes_): in the 256 lanes of a lockstep CTA / in a free warp */
+#ifndef ODE_B200_REFILL_IDLE
+#define ODE_B200_REFILL_IDLE 256
+#endif
+#ifndef ODE_B200_REFILL_IDLE_FREE
+#define ODE_B200_REFILL_IDLE_FREE 32
+#endif
+
 template <int N, int METHOD, bool DENSE>
 constexpr int min_blocks_for() {
 #ifdef ODE_B200_MIN_BLOCKS
     return ODE_B200_MIN_BLOCKS;
 #else
+    if (lockstep_for(N, METHOD)) return 1; /* one 8-warp CTA per SM, 255 registers */
     if (N <= 4) return DENSE ? 4 : 5; /* Dense/Continuous keep rcont[][] live: 96 registers spill */
     if (N > 8) return 3;
     if (METHOD == ODE_B200_DOP853) return DENSE ? 4 : 2;
@@ -58,6 +86,10 @@ struct Rk4Stepper {
     static constexpr int N = Sys::DIM;
     static constexpr bool kStage = STAGE;
     static constexpr int kMinBlocks = min_blocks_for<N, ODE_B200_RK4, false>();
+    static constexpr bool kSpec = spec_math_for<Sys, ODE_B200_RK4>();
+    static constexpr bool kLockstep = lockstep_for(N, ODE_B200_RK4);
+    static constexpr int kThreads = block_threads_for(N, ODE_B200_RK4);
+    static constexpr int kRefillIdle = kLockstep ? ODE_B200_REFILL_IDLE : ODE_B200_REFILL_IDLE_FREE;
     struct State {
         double y[N];
         double p[Sys::NP > 0 ? Sys::NP : 1];
@@ -85,34 +117,73 @@ struct Rk4Stepper {
         }
     }
 
+    static constexpr int NPP = Sys::NP > 0 ? Sys::NP : 1;
+    struct Work {
+        double k0[N], yn[N];
+    };
+    struct ColdIn {
+        double y[N], p[NPP], x, step;
+    };
+
+    /* Rk4::step, rk4.rs:103-132: the straight-line block (see MathFast) */
+    template <class M>
+    ODE_DEV static void core(const double (&y)[N], const double (&p)[NPP], double x, double step, Work& w, M& m) {
+        const double half = step / 2.0;
+        double k1[N], k2[N], k3[N], buf[N];
+        Sys::rhs(x, y, w.k0, p, m);
+#pragma unroll
+        for (int i = 0; i < N; ++i) buf[i] = y[i] + w.k0[i] * half;
+        Sys::rhs(x + half, buf, k1, p, m);
+#pragma unroll
+        for (int i = 0; i < N; ++i) buf[i] = y[i] + k1[i] * half;
+        Sys::rhs(x + half, buf, k2, p, m);
+#pragma unroll
+        for (int i = 0; i < N; ++i) buf[i] = y[i] + k2[i] * step;
+        Sys::rhs(x + step, buf, k3, p, m);
+        const double h6 = step / 6.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) w.yn[i] = y[i] + (((w.k0[i] + k1[i] * 2.0) + k2[i] * 2.0) + k3[i]) * h6;
+    }
+
+    static __device__ __noinline__ void core_exact(const ColdIn* in, Work* w) {
+        MathExact m;
+        core<MathExact>(in->y, in->p, in->x, in->step, *w, m);
+    }
+
     /* one Rk4::step + the loop body of integrate, rk4.rs:79-98,103-132 */
     ODE_DEV static bool attempt(State& s, const KernelArgs& a) {
         if (s.steps_left == 0) {
             store_final_<N>(a, s.traj, s.y, s.x, a.cfg.step_size, s.c, s.status, 0.0);
             return true;
         }
-        const double step = a.cfg.step_size, half = step / 2.0, x = s.x;
-        double k0[N], k1[N], k2[N], k3[N], buf[N], yn[N];
-        Sys::rhs(x, s.y, k0, s.p);
+        const double step = a.cfg.step_size, x = s.x;
+        Work w;
+        MathFast m;
+        if constexpr (kSpec) {
+            core<MathFast>(s.y, s.p, x, step, w, m);
+        } else {
+            MathExact mx;
+            core<MathExact>(s.y, s.p, x, step, w, mx);
+        }
+        if (__builtin_expect(kSpec && m.bad(), 0)) {
+            ColdIn in;
+            Work w2;
 #pragma unroll
-        for (int i = 0; i < N; ++i) buf[i] = s.y[i] + k0[i] * half;
-        Sys::rhs(x + half, buf, k1, s.p);
+            for (int i = 0; i < N; ++i) in.y[i] = s.y[i];
 #pragma unroll
-        for (int i = 0; i < N; ++i) buf[i] = s.y[i] + k1[i] * half;
-        Sys::rhs(x + half, buf, k2, s.p);
-#pragma unroll
-        for (int i = 0; i < N; ++i) buf[i] = s.y[i] + k2[i] * step;
-        Sys::rhs(x + step, buf, k3, s.p);
+            for (int i = 0; i < NPP; ++i) in.p[i] = s.p[i];
+            in.x = x;
+            in.step = step;
+            core_exact(&in, &w2);
+            w = w2;
+        }
         const double x_new = x + step;
-        const double h6 = step / 6.0;
-#pragma unroll
-        for (int i = 0; i < N; ++i) yn[i] = s.y[i] + (((k0[i] + k1[i] * 2.0) + k2[i] * 2.0) + k3[i]) * h6;
         bool stop = false;
-        if constexpr (Sys::HAS_SOLOUT) stop = Sys::solout(x_new, yn, k0, s.p);
+        if constexpr (Sys::HAS_SOLOUT) stop = Sys::solout(x_new, w.yn, w.k0, s.p);
         s.x = x_new;
 #pragma unroll
-        for (int i = 0; i < N; ++i) s.y[i] = yn[i];
-        push_<N, STAGE>(a, s.traj, s.c, x_new, yn);
+        for (int i = 0; i < N; ++i) s.y[i] = w.yn[i];
+        push_<N, STAGE>(a, s.traj, s.c, x_new, w.yn);
         s.c.num_eval += 4;
         s.c.accepted += 1;
         s.c.n_step += 1;
@@ -135,6 +206,10 @@ struct Dopri5Stepper {
     static constexpr bool CONT = OUT == ODE_B200_OUT_CONTINUOUS;
     static constexpr bool TRACK_LAST = DENSE && Sys::HAS_SOLOUT;
     static constexpr int kMinBlocks = min_blocks_for<N, ODE_B200_DOPRI5, DENSE || CONT>();
+    static constexpr bool kSpec = spec_math_for<Sys, ODE_B200_DOPRI5>();
+    static constexpr bool kLockstep = lockstep_for(N, ODE_B200_DOPRI5);
+    static constexpr int kThreads = block_threads_for(N, ODE_B200_DOPRI5);
+    static constexpr int kRefillIdle = kLockstep ? ODE_B200_REFILL_IDLE : ODE_B200_REFILL_IDLE_FREE;
 
     struct State {
         double y[N], k0[N]; /* k0 = f(x, y): first-same-as-last slot k[0] */
@@ -167,7 +242,7 @@ struct Dopri5Stepper {
         }
         s.h_old = s.h;
         if constexpr (OUT == ODE_B200_OUT_SPARSE) push_<N, STAGE>(a, t, s.c, s.x, s.y);
-        Sys::rhs(s.x, s.y, s.k0, s.p);
+        rhs_checked_<Sys>(s.x, s.y, s.k0, s.p);
         s.c.num_eval += 1;
     }
 
@@ -176,6 +251,71 @@ struct Dopri5Stepper {
 #pragma unroll
         for (int i = 0; i < N; ++i)
             o[i] = rc[0][i] + (rc[1][i] + (rc[2][i] + (rc[3][i] + rc[4][i] * th1) * th) * th1) * th;
+    }
+
+    static constexpr int NPP = Sys::NP > 0 ? Sys::NP : 1;
+    /* everything one attempted step computes before the accept / reject decision */
+    struct Work {
+        double k[7][N]; /* k[0] = f(x, y); k[s] for s = 1..6, k[6] is the reference's new k[1] */
+        double ynext[N];
+        double err;
+        CtrlEval ce;
+    };
+    struct ColdIn {
+        double y[N], k0[N], p[NPP], x, h, pw_old;
+    };
+
+    /* the straight-line block of one attempt (see MathFast): 6 stages, error norm, controller */
+    template <class M>
+    ODE_DEV static void core(const double (&y)[N], const double (&k0)[N], const double (&p)[NPP], double pw_old,
+                             const KernelArgs& a, double x, double h, Work& w, M& m) {
+        const ode_b200_config& cfg = a.cfg;
+        double(&k)[7][N] = w.k;
+        double(&ynext)[N] = w.ynext;
+        /* 6 stages, dopri5.rs:326-340 */
+        bool bad = false;
+#pragma unroll
+        for (int i = 0; i < N; ++i) k[0][i] = k0[i];
+        static_for<1, 7>([&](auto S) {
+            constexpr int sg = decltype(S)::value;
+#pragma unroll
+            for (int i = 0; i < N; ++i) ynext[i] = y[i];
+            static_for<0, sg>([&](auto J) {
+                constexpr int j = decltype(J)::value;
+                constexpr double aij = TabDp5::a(sg, j);
+                if constexpr (aij != 0.0) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) ynext[i] = ynext[i] + (k[j][i] * h) * c_dp5_a[sg][j];
+                }
+            });
+            Sys::rhs(x + h * c_dp5_c[sg], ynext, k[sg], p, m);
+            if constexpr (sg == 1) { /* only k2 meets structural zeros (a72, e2, d2): see header note */
+#pragma unroll
+                for (int i = 0; i < N; ++i) bad |= nonfinite_(k[sg][i]);
+            }
+        });
+        /* error estimate and norm, dopri5.rs:354-371 */
+        double err = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double ee = (((((k[0][i] * c_dp5_e[0] + k[2][i] * c_dp5_e[2]) + k[3][i] * c_dp5_e[3]) +
+                                 k[4][i] * c_dp5_e[4]) +
+                                k[5][i] * c_dp5_e[5]) +
+                               k[6][i] * c_dp5_e[6]) *
+                              h;
+            const double sc = cfg.atol + fmax(fabs(y[i]), fabs(ynext[i])) * cfg.rtol;
+            const double q = m.div(ee, sc);
+            err += q * q;
+        }
+        err = m.sqrt(m.div(err, (double)N));
+        if (bad) err = qnan_();
+        w.err = err;
+        ctrl_eval_(pw_old, a, err, h, m, w.ce);
+    }
+
+    static __device__ __noinline__ void core_exact(const ColdIn* in, const KernelArgs* a, Work* w) {
+        MathExact m;
+        core<MathExact>(in->y, in->k0, in->p, in->pw_old, *a, in->x, in->h, *w, m);
     }
 
     /* one pass of `while !last`, dopri5.rs:299-443 */
@@ -197,49 +337,36 @@ struct Dopri5Stepper {
         s.c.n_step += 1;
         const double h = s.h, x = s.x;
 
-        /* 6 stages, dopri5.rs:326-340. k[s] for s = 1..6; k[6] is the reference's new k[1]. */
-        double k[7][N], ynext[N];
-        bool bad = false;
-#pragma unroll
-        for (int i = 0; i < N; ++i) k[0][i] = s.k0[i];
-        static_for<1, 7>([&](auto S) {
-            constexpr int sg = decltype(S)::value;
-#pragma unroll
-            for (int i = 0; i < N; ++i) ynext[i] = s.y[i];
-            static_for<0, sg>([&](auto J) {
-                constexpr int j = decltype(J)::value;
-                constexpr double aij = TabDp5::a(sg, j);
-                if constexpr (aij != 0.0) {
-#pragma unroll
-                    for (int i = 0; i < N; ++i) ynext[i] = ynext[i] + (k[j][i] * h) * c_dp5_a[sg][j];
-                }
-            });
-            Sys::rhs(x + h * c_dp5_c[sg], ynext, k[sg], s.p);
-            if constexpr (sg == 1) { /* only k2 meets structural zeros (a72, e2, d2): see header note */
-#pragma unroll
-                for (int i = 0; i < N; ++i) bad |= nonfinite_(k[sg][i]);
-            }
-        });
-        s.c.num_eval += 6;
-
-        /* error estimate and norm, dopri5.rs:354-371 */
-        double err = 0.0;
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            const double ee = (((((k[0][i] * c_dp5_e[0] + k[2][i] * c_dp5_e[2]) + k[3][i] * c_dp5_e[3]) +
-                                 k[4][i] * c_dp5_e[4]) +
-                                k[5][i] * c_dp5_e[5]) +
-                               k[6][i] * c_dp5_e[6]) *
-                              h;
-            const double sc = cfg.atol + fmax(fabs(s.y[i]), fabs(ynext[i])) * cfg.rtol;
-            const double q = ee / sc;
-            err += q * q;
+        Work w;
+        MathFast m;
+        if constexpr (kSpec) {
+            core<MathFast>(s.y, s.k0, s.p, s.ctrl.pw_old, a, x, h, w, m);
+        } else {
+            MathExact mx;
+            core<MathExact>(s.y, s.k0, s.p, s.ctrl.pw_old, a, x, h, w, mx);
         }
-        err = sqrt(err / (double)N);
-        if (bad) err = qnan_();
+        if (__builtin_expect(kSpec && m.bad(), 0)) { /* some operand left the fast paths' window: redo it exactly */
+            ColdIn in;
+            Work w2;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                in.y[i] = s.y[i];
+                in.k0[i] = s.k0[i];
+            }
+#pragma unroll
+            for (int i = 0; i < NPP; ++i) in.p[i] = s.p[i];
+            in.x = x;
+            in.h = h;
+            in.pw_old = s.ctrl.pw_old;
+            core_exact(&in, &a, &w2);
+            w = w2;
+        }
+        s.c.num_eval += 6;
+        double(&k)[7][N] = w.k;
+        double(&ynext)[N] = w.ynext;
 
         double h_new;
-        if (ctrl_accept_(s.ctrl, a, err, h, h_new)) {
+        if (ctrl_commit_(s.ctrl, a, w.ce, w.err, h, h_new)) {
             s.c.accepted += 1;
             /* stiffness detection, dopri5.rs:378-402 (accepted % n_stiff == 0 kept as a counter) */
             if (++s.stiff_ctr == cfg.n_stiff) s.stiff_ctr = 0;
@@ -380,6 +507,10 @@ struct Dop853Stepper {
     static constexpr bool CONT8 = OUT == ODE_B200_OUT_CONTINUOUS8;
     static constexpr bool TRACK_LAST = DENSE && Sys::HAS_SOLOUT;
     static constexpr int kMinBlocks = min_blocks_for<N, ODE_B200_DOP853, DENSE || CONT8>();
+    static constexpr bool kSpec = spec_math_for<Sys, ODE_B200_DOP853>();
+    static constexpr bool kLockstep = lockstep_for(N, ODE_B200_DOP853);
+    static constexpr int kThreads = block_threads_for(N, ODE_B200_DOP853);
+    static constexpr int kRefillIdle = kLockstep ? ODE_B200_REFILL_IDLE : ODE_B200_REFILL_IDLE_FREE;
 
     struct State {
         double y[N], k0[N]; /* k0 = reference k[0] = f(x, y) */
@@ -435,8 +566,102 @@ struct Dop853Stepper {
         } else {
             push_<N, STAGE>(a, t, s.c, a.cfg.x0, s.y);
         }
-        Sys::rhs(s.x, s.y, s.k0, s.p);
+        rhs_checked_<Sys>(s.x, s.y, s.k0, s.p);
         s.c.num_eval += 1;
+    }
+
+    static constexpr int NPP = Sys::NP > 0 ? Sys::NP : 1;
+    /* everything one attempted step computes before the accept / reject decision */
+    struct Work {
+        double k[12][N]; /* k[0] = f(x, y); k[s] = stage s+1. Reference slots after the stage loop:
+                            k[1] = k11 (our k[10]), k[2] = k12 (our k[11]) */
+        double ynext[N]; /* argument of stage 12 (stiffness test) */
+        double y8[N];    /* 8th-order solution, reference k[4] */
+        double err;
+        CtrlEval ce;
+    };
+    struct ColdIn {
+        double y[N], k0[N], p[NPP], x, h, pw_old;
+    };
+
+    /* the straight-line block of one attempt (see MathFast): 11 stages, 8th-order solution, the
+     * two error estimators, controller */
+    template <class M>
+    ODE_DEV static void core(const double (&y)[N], const double (&k0)[N], const double (&p)[NPP], double pw_old,
+                             const KernelArgs& a, double x, double h, Work& w, M& m) {
+        const ode_b200_config& cfg = a.cfg;
+        double(&k)[12][N] = w.k;
+        double(&ynext)[N] = w.ynext;
+        double(&y8)[N] = w.y8;
+        /* stages 2..12, dop853.rs:307-321: k[s] = f(x + h*c(s+1), y + sum_j k[j]*(h*a(s+1,j+1))) */
+        bool bad = false;
+#pragma unroll
+        for (int i = 0; i < N; ++i) k[0][i] = k0[i];
+        static_for<1, 12>([&](auto S) {
+            constexpr int sg = decltype(S)::value;
+#pragma unroll
+            for (int i = 0; i < N; ++i) ynext[i] = y[i];
+            static_for<0, sg>([&](auto J) {
+                constexpr int j = decltype(J)::value;
+                constexpr double aij = TabDp8::a(sg, j);
+                if constexpr (aij != 0.0) {
+                    const double ha = h * c_dp8_a[sg][j];
+#pragma unroll
+                    for (int i = 0; i < N; ++i) ynext[i] = ynext[i] + k[j][i] * ha;
+                }
+            });
+            Sys::rhs(x + (h * c_dp8_c[sg]), ynext, k[sg], p, m); /* c(12) = 0.0 (Q1) */
+            if constexpr (sg >= 1 && sg <= 4) { /* only k2..k5 have b = e = 0: see header note */
+#pragma unroll
+                for (int i = 0; i < N; ++i) bad |= nonfinite_(k[sg][i]);
+            }
+        });
+
+        /* 8th-order solution, dop853.rs:323-331 */
+        double bsum[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            bsum[i] = ((((((k[0][i] * c_dp8_b[0] + k[5][i] * c_dp8_b[5]) + k[6][i] * c_dp8_b[6]) +
+                          k[7][i] * c_dp8_b[7]) +
+                         k[8][i] * c_dp8_b[8]) +
+                        k[9][i] * c_dp8_b[9]) +
+                       k[10][i] * c_dp8_b[10]) +
+                      k[11][i] * c_dp8_b[11];
+            y8[i] = y[i] + bsum[i] * h;
+        }
+        /* error estimators and norm, dop853.rs:334-362. err_est runs over the 12 slots; slots
+         * 1..4 (k11, k12, bsum, y8) meet e2..e5 = 0 and are skipped. */
+        double err = 0.0, err2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double ee = k[0][i] * c_dp8_e[0]; /* 0.0 + v == v */
+            ee = ee + k[5][i] * c_dp8_e[5];
+            ee = ee + k[6][i] * c_dp8_e[6];
+            ee = ee + k[7][i] * c_dp8_e[7];
+            ee = ee + k[8][i] * c_dp8_e[8];
+            ee = ee + k[9][i] * c_dp8_e[9];
+            ee = ee + k[10][i] * c_dp8_e[10];
+            ee = ee + k[11][i] * c_dp8_e[11];
+            const double eb = ((bsum[i] - k[0][i] * c_dp8_bhh[0]) - k[8][i] * c_dp8_bhh[1]) -
+                              k[11][i] * c_dp8_bhh[2];
+            const double sc = cfg.atol + fmax(fabs(y[i]), fabs(y8[i])) * cfg.rtol;
+            /* err_est_i / sc_i and err_bhh_i / sc_i: one refined reciprocal, two exact quotients */
+            const double rsc = m.rcp(sc);
+            const double q1 = m.div_by(ee, sc, rsc), q2 = m.div_by(eb, sc, rsc);
+            err += q1 * q1;
+            err2 += q2 * q2;
+        }
+        double deno = err + 0.01 * err2;
+        if (deno <= 0.0) deno = 1.0;
+        err = fabs(h) * err * m.sqrt_nz(m.div_nz(1.0, deno * (double)N));
+        if (bad) err = qnan_();
+        w.err = err;
+        ctrl_eval_(pw_old, a, err, h, m, w.ce);
+    }
+
+    static __device__ __noinline__ void core_exact(const ColdIn* in, const KernelArgs* a, Work* w) {
+        MathExact m;
+        core<MathExact>(in->y, in->k0, in->p, in->pw_old, *a, in->x, in->h, *w, m);
     }
 
     /* one pass of `while !last`, dop853.rs:281-510 */
@@ -458,78 +683,40 @@ struct Dop853Stepper {
         s.c.n_step += 1;
         const double h = s.h, x = s.x;
 
-        /* stages 2..12, dop853.rs:307-321: k[s] = f(x + h*c(s+1), y + sum_j k[j]*(h*a(s+1,j+1))) */
-        double k[12][N], ynext[N];
-        bool bad = false;
+        Work w;
+        MathFast m;
+        if constexpr (kSpec) {
+            core<MathFast>(s.y, s.k0, s.p, s.ctrl.pw_old, a, x, h, w, m);
+        } else {
+            MathExact mx;
+            core<MathExact>(s.y, s.k0, s.p, s.ctrl.pw_old, a, x, h, w, mx);
+        }
+        if (__builtin_expect(kSpec && m.bad(), 0)) { /* some operand left the fast paths' window: redo it exactly */
+            ColdIn in;
+            Work w2;
 #pragma unroll
-        for (int i = 0; i < N; ++i) k[0][i] = s.k0[i];
-        static_for<1, 12>([&](auto S) {
-            constexpr int sg = decltype(S)::value;
-#pragma unroll
-            for (int i = 0; i < N; ++i) ynext[i] = s.y[i];
-            static_for<0, sg>([&](auto J) {
-                constexpr int j = decltype(J)::value;
-                constexpr double aij = TabDp8::a(sg, j);
-                if constexpr (aij != 0.0) {
-                    const double ha = h * c_dp8_a[sg][j];
-#pragma unroll
-                    for (int i = 0; i < N; ++i) ynext[i] = ynext[i] + k[j][i] * ha;
-                }
-            });
-            Sys::rhs(x + (h * c_dp8_c[sg]), ynext, k[sg], s.p); /* c(12) = 0.0 (Q1) */
-            if constexpr (sg >= 1 && sg <= 4) { /* only k2..k5 have b = e = 0: see header note */
-#pragma unroll
-                for (int i = 0; i < N; ++i) bad |= nonfinite_(k[sg][i]);
+            for (int i = 0; i < N; ++i) {
+                in.y[i] = s.y[i];
+                in.k0[i] = s.k0[i];
             }
-        });
+#pragma unroll
+            for (int i = 0; i < NPP; ++i) in.p[i] = s.p[i];
+            in.x = x;
+            in.h = h;
+            in.pw_old = s.ctrl.pw_old;
+            core_exact(&in, &a, &w2);
+            w = w2;
+        }
         s.c.num_eval += 11;
-        /* from here the reference's slots are: k[1] = k11 (our k[10]), k[2] = k12 (our k[11]) */
-
-        /* 8th-order solution, dop853.rs:323-331 */
-        double bsum[N], y8[N];
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            bsum[i] = ((((((k[0][i] * c_dp8_b[0] + k[5][i] * c_dp8_b[5]) + k[6][i] * c_dp8_b[6]) +
-                          k[7][i] * c_dp8_b[7]) +
-                         k[8][i] * c_dp8_b[8]) +
-                        k[9][i] * c_dp8_b[9]) +
-                       k[10][i] * c_dp8_b[10]) +
-                      k[11][i] * c_dp8_b[11];
-            y8[i] = s.y[i] + bsum[i] * h;
-        }
-        /* error estimators and norm, dop853.rs:334-362. err_est runs over the 12 slots; slots
-         * 1..4 (k11, k12, bsum, y8) meet e2..e5 = 0 and are skipped. */
-        double err = 0.0, err2 = 0.0;
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            double ee = k[0][i] * c_dp8_e[0]; /* 0.0 + v == v */
-            ee = ee + k[5][i] * c_dp8_e[5];
-            ee = ee + k[6][i] * c_dp8_e[6];
-            ee = ee + k[7][i] * c_dp8_e[7];
-            ee = ee + k[8][i] * c_dp8_e[8];
-            ee = ee + k[9][i] * c_dp8_e[9];
-            ee = ee + k[10][i] * c_dp8_e[10];
-            ee = ee + k[11][i] * c_dp8_e[11];
-            const double eb = ((bsum[i] - k[0][i] * c_dp8_bhh[0]) - k[8][i] * c_dp8_bhh[1]) -
-                              k[11][i] * c_dp8_bhh[2];
-            const double sc = cfg.atol + fmax(fabs(s.y[i]), fabs(y8[i])) * cfg.rtol;
-            /* err_est_i / sc_i and err_bhh_i / sc_i: one refined reciprocal, two exact quotients */
-            const double rsc = div_rcp_(sc);
-            const bool sc_ok = div_in_range_(sc);
-            const double q1 = div_with_rcp_(ee, sc, rsc, sc_ok), q2 = div_with_rcp_(eb, sc, rsc, sc_ok);
-            err += q1 * q1;
-            err2 += q2 * q2;
-        }
-        double deno = err + 0.01 * err2;
-        if (deno <= 0.0) deno = 1.0;
-        err = fabs(h) * err * sqrt(1.0 / (deno * (double)N));
-        if (bad) err = qnan_();
+        double(&k)[12][N] = w.k;
+        double(&ynext)[N] = w.ynext;
+        double(&y8)[N] = w.y8;
 
         double h_new;
-        if (ctrl_accept_(s.ctrl, a, err, h, h_new)) {
+        if (ctrl_commit_(s.ctrl, a, w.ce, w.err, h, h_new)) {
             s.c.accepted += 1;
             double knew[N]; /* reference k[3] = f(x + h, k[4]); no FSAL reuse (Q11) */
-            Sys::rhs(x + h, y8, knew, s.p);
+            rhs_checked_<Sys>(x + h, y8, knew, s.p);
             s.c.num_eval += 1;
 
             /* stiffness detection, dop853.rs:372-396 */
@@ -590,7 +777,7 @@ struct Dop853Stepper {
                                         k[11][i] * c_dp8_a[13][11]) +
                                        knew[i] * c_dp8_a[13][12]) *
                                           h;
-                Sys::rhs(x + h * c_dp8_c[13], yy, k14, s.p);
+                rhs_checked_<Sys>(x + h * c_dp8_c[13], yy, k14, s.p);
 #pragma unroll
                 for (int i = 0; i < N; ++i)
                     yy[i] = s.y[i] + (((((((k[0][i] * c_dp8_a[14][0] + k[5][i] * c_dp8_a[14][5]) +
@@ -601,7 +788,7 @@ struct Dop853Stepper {
                                         knew[i] * c_dp8_a[14][12]) +
                                        k14[i] * c_dp8_a[14][13]) *
                                           h;
-                Sys::rhs(x + h * c_dp8_c[14], yy, k15, s.p);
+                rhs_checked_<Sys>(x + h * c_dp8_c[14], yy, k15, s.p);
 #pragma unroll
                 for (int i = 0; i < N; ++i)
                     yy[i] = s.y[i] + (((((((k[0][i] * c_dp8_a[15][0] + k[5][i] * c_dp8_a[15][5]) +
@@ -612,7 +799,7 @@ struct Dop853Stepper {
                                         k14[i] * c_dp8_a[15][13]) +
                                        k15[i] * c_dp8_a[15][14]) *
                                           h;
-                Sys::rhs(x + h * c_dp8_c[15], yy, k16, s.p);
+                rhs_checked_<Sys>(x + h * c_dp8_c[15], yy, k16, s.p);
                 s.c.num_eval += 3;
                 static_for<0, 4>([&](auto R) {
                     constexpr int r = decltype(R)::value;
@@ -720,6 +907,9 @@ template <class Sys>
 struct Rk4StepperF32 {
     static constexpr int N = Sys::DIM;
     static constexpr bool kStage = false;
+    static constexpr bool kLockstep = false;
+    static constexpr int kRefillIdle = 1;
+    static constexpr int kThreads = 128;
     static constexpr int kMinBlocks = 5;
     struct State {
         float y[N];
@@ -785,16 +975,17 @@ struct Rk4StepperF32 {
         if (s.steps_left == 0) return finish(a, s);
         const float step = a.step_size, half = step / 2.0f, x = s.x;
         float k0[N], k1[N], k2[N], k3[N], buf[N], yn[N];
-        Sys::rhs(x, s.y, k0, s.p);
+        MathExact mx;
+        Sys::rhs(x, s.y, k0, s.p, mx);
 #pragma unroll
         for (int i = 0; i < N; ++i) buf[i] = s.y[i] + k0[i] * half;
-        Sys::rhs(x + half, buf, k1, s.p);
+        Sys::rhs(x + half, buf, k1, s.p, mx);
 #pragma unroll
         for (int i = 0; i < N; ++i) buf[i] = s.y[i] + k1[i] * half;
-        Sys::rhs(x + half, buf, k2, s.p);
+        Sys::rhs(x + half, buf, k2, s.p, mx);
 #pragma unroll
         for (int i = 0; i < N; ++i) buf[i] = s.y[i] + k2[i] * step;
-        Sys::rhs(x + step, buf, k3, s.p);
+        Sys::rhs(x + step, buf, k3, s.p, mx);
         const float x_new = x + step;
         const float h6 = step / 6.0f;
 #pragma unroll
@@ -815,13 +1006,13 @@ struct Rk4StepperF32 {
 };
 
 template <class Sys>
-__global__ void __launch_bounds__(kBlockThreads, 5) ode_rk4_f32_kernel(const __grid_constant__ KernelArgsF32 a) {
+__global__ void __launch_bounds__(128, 5) ode_rk4_f32_kernel(const __grid_constant__ KernelArgsF32 a) {
     run_lanes_<Rk4StepperF32<Sys>>(a);
 }
 
 /* ============================================================================ kernels */
 template <class Stepper>
-__global__ void __launch_bounds__(kBlockThreads, Stepper::kMinBlocks) ode_step_loop_kernel(const __grid_constant__ KernelArgs a) {
+__global__ void __launch_bounds__(Stepper::kThreads, Stepper::kMinBlocks) ode_step_loop_kernel(const __grid_constant__ KernelArgs a) {
     run_lanes_<Stepper>(a);
 }
 

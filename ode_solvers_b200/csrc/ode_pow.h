@@ -139,6 +139,32 @@ ODE_POW_SLOW double ode_exp_specialcase_(double tmp, ode_u64 sbits, ode_u64 ki) 
     return 0x1p-1022 * y;
 }
 
+/* The main path of exp_inline below as straight-line code: exp(x + xtail) * (-1)^(sign_bias != 0)
+ * for 2^-54 <= |x| < 512 (ode_exp_in_main_range_), where no special case applies and the scale
+ * needs no adjustment. The step-loop kernels run it speculatively and test the range afterwards. */
+ODE_POW_FN int ode_exp_in_main_range_(double x) {
+    return ((ode_u32)(ODE_ASU64(x) >> 52) & 0x7ff) - 0x3c9u < 0x3fu;
+}
+ODE_POW_FN double ode_exp_main_(double x, double xtail, ode_u32 sign_bias, ode_pow_tabs T) {
+    double kd = fma(x, K_INVLN2N, K_SHIFT);
+    ode_u64 ki = ODE_ASU64(kd);
+    kd -= K_SHIFT;
+    double r = fma(kd, K_NEGLN2HIN, x);
+    r = fma(kd, K_NEGLN2LON, r);
+    r += xtail;
+    ode_u32 idx = 2u * (ode_u32)(ki & 127u);
+    ode_u64 top = (ki + sign_bias) << 45;
+    double tail = ODE_ASF64(T.et[idx]);
+    ode_u64 sbits = T.et[idx + 1] + top;
+    double r2 = r * r;
+    double p01 = fma(r, K_C3, K_C2);
+    double p23 = fma(r, K_C5, K_C4);
+    double tmp = fma(p01, r2, tail + r);
+    tmp = fma(r2 * r2, p23, tmp);
+    double scale = ODE_ASF64(sbits);
+    return fma(scale, tmp, scale);
+}
+
 /* exp(x + xtail) * (-1)^(sign_bias != 0); shared by pow and exp. */
 ODE_POW_FN double ode_exp_inline_(double x, double xtail, ode_u32 sign_bias, int has_tail, ode_pow_tabs T) {
     ode_u32 abstop = (ode_u32)(ODE_ASU64(x) >> 52) & 0x7ff;

@@ -22,9 +22,10 @@ namespace ode_b200 {
 /* examples/lorenz.rs:42-54 ; p = {sigma, beta, rho} */
 struct SysLorenz {
     static constexpr int DIM = 3, NP = 3;
+    static constexpr bool SPEC = false;
     static constexpr bool HAS_SOLOUT = false, HAS_F32 = true;
-    template <class T>
-    ODE_DEV static void rhs(T, const T* y, T* dy, const T* p) {
+    template <class T, class M>
+    ODE_DEV static void rhs(T, const T* y, T* dy, const T* p, M&) {
         dy[0] = p[0] * (y[1] - y[0]);
         dy[1] = y[0] * (p[2] - y[2]) - y[1];
         dy[2] = y[0] * y[1] - p[1] * y[2];
@@ -36,19 +37,20 @@ struct SysLorenz {
 /* examples/kepler_orbit.rs:51-66 ; p = {mu} */
 struct SysKepler {
     static constexpr int DIM = 6, NP = 1;
+    static constexpr bool SPEC = true;
     static constexpr bool HAS_SOLOUT = false, HAS_F32 = false;
-    ODE_DEV static void rhs(double, const double* y, double* dy, const double* p) {
-        const double r = sqrt(y[0] * y[0] + y[1] * y[1] + y[2] * y[2]);
+    template <class M>
+    ODE_DEV static void rhs(double, const double* y, double* dy, const double* p, M& m) {
+        const double r = m.sqrt_nz(y[0] * y[0] + y[1] * y[1] + y[2] * y[2]);
         const double r3 = r * r * r;
         /* three exact IEEE quotients by the same r3: one refined reciprocal (ode_device.cuh) */
-        const double ir3 = div_rcp_(r3);
-        const bool ok = div_in_range_(r3);
+        const double ir3 = m.rcp(r3);
         dy[0] = y[3];
         dy[1] = y[4];
         dy[2] = y[5];
-        dy[3] = div_with_rcp_(-p[0] * y[0], r3, ir3, ok);
-        dy[4] = div_with_rcp_(-p[0] * y[1], r3, ir3, ok);
-        dy[5] = div_with_rcp_(-p[0] * y[2], r3, ir3, ok);
+        dy[3] = m.div_by(-p[0] * y[0], r3, ir3);
+        dy[4] = m.div_by(-p[0] * y[1], r3, ir3);
+        dy[5] = m.div_by(-p[0] * y[2], r3, ir3);
     }
     ODE_DEV static bool solout(double, const double*, const double*, const double*) { return false; }
 };
@@ -56,19 +58,23 @@ struct SysKepler {
 /* examples/three_body_system.rs:40-59 (circular restricted three-body problem) ; p = {mu} */
 struct SysCr3bp {
     static constexpr int DIM = 6, NP = 1;
+    static constexpr bool SPEC = true;
     static constexpr bool HAS_SOLOUT = false, HAS_F32 = false;
-    ODE_DEV static void rhs(double, const double* y, double* dy, const double* p) {
+    template <class M>
+    ODE_DEV static void rhs(double, const double* y, double* dy, const double* p, M& m) {
         const double mu = p[0];
         const double a = y[0] + mu, b = y[0] - 1.0 + mu;
-        const double d = sqrt(a * a + y[1] * y[1] + y[2] * y[2]);
-        const double r = sqrt(b * b + y[1] * y[1] + y[2] * y[2]);
+        const double d = m.sqrt_nz(a * a + y[1] * y[1] + y[2] * y[2]);
+        const double r = m.sqrt_nz(b * b + y[1] * y[1] + y[2] * y[2]);
         const double d3 = d * d * d, r3 = r * r * r;
+        const double id3 = m.rcp(d3), ir3 = m.rcp(r3); /* one refined reciprocal per denominator */
         dy[0] = y[3];
         dy[1] = y[4];
         dy[2] = y[5];
-        dy[3] = y[0] + 2.0 * y[4] - (1.0 - mu) * (y[0] + mu) / d3 - mu * (y[0] - 1.0 + mu) / r3;
-        dy[4] = -2.0 * y[3] + y[1] - (1.0 - mu) * y[1] / d3 - mu * y[1] / r3;
-        dy[5] = -(1.0 - mu) * y[2] / d3 - mu * y[2] / r3;
+        dy[3] = y[0] + 2.0 * y[4] - m.div_by((1.0 - mu) * (y[0] + mu), d3, id3) -
+                m.div_by(mu * (y[0] - 1.0 + mu), r3, ir3);
+        dy[4] = -2.0 * y[3] + y[1] - m.div_by((1.0 - mu) * y[1], d3, id3) - m.div_by(mu * y[1], r3, ir3);
+        dy[5] = m.div_by(-(1.0 - mu) * y[2], d3, id3) - m.div_by(mu * y[2], r3, ir3);
     }
     ODE_DEV static bool solout(double, const double*, const double*, const double*) { return false; }
 };
@@ -77,9 +83,10 @@ struct SysCr3bp {
  * p = {k1, k2, k3}; p = (0.04, 1e4, 3e7) is bitwise the example */
 struct SysRobertson {
     static constexpr int DIM = 3, NP = 3;
+    static constexpr bool SPEC = false;
     static constexpr bool HAS_SOLOUT = false, HAS_F32 = true;
-    template <class T>
-    ODE_DEV static void rhs(T, const T* y, T* dy, const T* p) {
+    template <class T, class M>
+    ODE_DEV static void rhs(T, const T* y, T* dy, const T* p, M&) {
         dy[0] = -p[0] * y[0] + p[1] * y[1] * y[2];
         dy[1] = p[0] * y[0] - p[1] * y[1] * y[2] - p[2] * y[1] * y[1];
         dy[2] = p[2] * y[1] * y[1];
@@ -91,9 +98,10 @@ struct SysRobertson {
 /* examples/bouncing_ball.rs:74-86 in f64 ; p = {g}. dy[2] = 0 written explicitly (Q13). */
 struct SysBouncingBall {
     static constexpr int DIM = 3, NP = 1;
+    static constexpr bool SPEC = false;
     static constexpr bool HAS_SOLOUT = true, HAS_F32 = true;
-    template <class T>
-    ODE_DEV static void rhs(T, const T* y, T* dy, const T* p) {
+    template <class T, class M>
+    ODE_DEV static void rhs(T, const T* y, T* dy, const T* p, M&) {
         dy[0] = y[1];
         dy[1] = -p[0];
         dy[2] = T(0);
@@ -106,8 +114,10 @@ struct SysBouncingBall {
  * oracle/ode_oracle_systems.c threebody18_rhs) ; p = {G*m1, G*m2, G*m3} */
 struct SysThreeBody18 {
     static constexpr int DIM = 18, NP = 3;
+    static constexpr bool SPEC = true;
     static constexpr bool HAS_SOLOUT = false, HAS_F32 = false;
-    ODE_DEV static void rhs(double, const double* y, double* dy, const double* p) {
+    template <class M>
+    ODE_DEV static void rhs(double, const double* y, double* dy, const double* p, M& m) {
 #pragma unroll
         for (int c = 0; c < 9; ++c) dy[c] = y[9 + c];
 #pragma unroll
@@ -119,8 +129,8 @@ struct SysThreeBody18 {
                 const double dx = y[3 * b] - y[3 * a], dyy = y[3 * b + 1] - y[3 * a + 1],
                              dz = y[3 * b + 2] - y[3 * a + 2];
                 const double r2 = dx * dx + dyy * dyy + dz * dz;
-                const double r = sqrt(r2);
-                const double inv = 1.0 / (r2 * r);
+                const double r = m.sqrt_nz(r2);
+                const double inv = m.div_nz(1.0, r2 * r);
                 const double fa = p[b] * inv, fb = p[a] * inv;
                 dy[9 + 3 * a] = dy[9 + 3 * a] + fa * dx;
                 dy[9 + 3 * a + 1] = dy[9 + 3 * a + 1] + fa * dyy;
@@ -136,9 +146,10 @@ struct SysThreeBody18 {
 /* src/rk4.rs:178-186 Test1 */
 struct SysTestRk4_1 {
     static constexpr int DIM = 1, NP = 0;
+    static constexpr bool SPEC = false;
     static constexpr bool HAS_SOLOUT = false, HAS_F32 = true;
-    template <class T>
-    ODE_DEV static void rhs(T x, const T* y, T* dy, const T*) { dy[0] = (x - y[0]) / T(2); }
+    template <class T, class M>
+    ODE_DEV static void rhs(T x, const T* y, T* dy, const T*, M&) { dy[0] = (x - y[0]) / T(2); }
     template <class T>
     ODE_DEV static bool solout(T, const T*, const T*, const T*) { return false; }
 };
@@ -146,9 +157,10 @@ struct SysTestRk4_1 {
 /* src/rk4.rs:188-196 Test2 */
 struct SysTestRk4_2 {
     static constexpr int DIM = 1, NP = 0;
+    static constexpr bool SPEC = false;
     static constexpr bool HAS_SOLOUT = false, HAS_F32 = true;
-    template <class T>
-    ODE_DEV static void rhs(T x, const T* y, T* dy, const T*) { dy[0] = T(-2) * x - y[0]; }
+    template <class T, class M>
+    ODE_DEV static void rhs(T x, const T* y, T* dy, const T*, M&) { dy[0] = T(-2) * x - y[0]; }
     template <class T>
     ODE_DEV static bool solout(T, const T*, const T*, const T*) { return false; }
 };
@@ -156,8 +168,10 @@ struct SysTestRk4_2 {
 /* src/rk4.rs:198-206 Test3 (= dopri5.rs:531-538, dop853.rs:595-602): uses f64::exp -> exp_d */
 struct SysTestExp {
     static constexpr int DIM = 1, NP = 0;
+    static constexpr bool SPEC = false;
     static constexpr bool HAS_SOLOUT = false, HAS_F32 = false;
-    ODE_DEV static void rhs(double x, const double* y, double* dy, const double*) {
+    template <class M>
+    ODE_DEV static void rhs(double x, const double* y, double* dy, const double*, M&) {
         dy[0] = (5.0 * x * x - y[0]) / exp_d(x + y[0]);
     }
     ODE_DEV static bool solout(double, const double*, const double*, const double*) { return false; }
@@ -166,8 +180,10 @@ struct SysTestExp {
 /* the same with `solout: x >= 0.5` (rk4.rs:219-221, dopri5.rs:540-542, dop853.rs:604-606) ; p = {x_stop} */
 struct SysTestExpStop {
     static constexpr int DIM = 1, NP = 1;
+    static constexpr bool SPEC = false;
     static constexpr bool HAS_SOLOUT = true, HAS_F32 = false;
-    ODE_DEV static void rhs(double x, const double* y, double* dy, const double*) {
+    template <class M>
+    ODE_DEV static void rhs(double x, const double* y, double* dy, const double*, M&) {
         dy[0] = (5.0 * x * x - y[0]) / exp_d(x + y[0]);
     }
     ODE_DEV static bool solout(double x, const double*, const double*, const double* p) { return x >= p[0]; }
@@ -176,8 +192,10 @@ struct SysTestExpStop {
 /* tests/dopri5.rs:13-19 : y' = -3 t^2 e^y */
 struct SysTestCubic {
     static constexpr int DIM = 1, NP = 0;
+    static constexpr bool SPEC = false;
     static constexpr bool HAS_SOLOUT = false, HAS_F32 = false;
-    ODE_DEV static void rhs(double x, const double* y, double* dy, const double*) {
+    template <class M>
+    ODE_DEV static void rhs(double x, const double* y, double* dy, const double*, M&) {
         dy[0] = -3.0 * x * x * exp_d(y[0]);
     }
     ODE_DEV static bool solout(double, const double*, const double*, const double*) { return false; }
@@ -186,8 +204,10 @@ struct SysTestCubic {
 /* tests/dopri5.rs:21-31 with `solout: x >= 4.1` ; p = {x_stop} */
 struct SysTestCubicStop {
     static constexpr int DIM = 1, NP = 1;
+    static constexpr bool SPEC = false;
     static constexpr bool HAS_SOLOUT = true, HAS_F32 = false;
-    ODE_DEV static void rhs(double x, const double* y, double* dy, const double*) {
+    template <class M>
+    ODE_DEV static void rhs(double x, const double* y, double* dy, const double*, M&) {
         dy[0] = -3.0 * x * x * exp_d(y[0]);
     }
     ODE_DEV static bool solout(double x, const double*, const double*, const double* p) { return x >= p[0]; }
