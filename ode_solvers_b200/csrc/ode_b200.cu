@@ -860,11 +860,27 @@ __global__ void debug_pow_kernel(long long n, const double* x, const double* y, 
 __global__ void debug_div_kernel(long long n, const double* a, const double* b, double* o, int shared_den) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    if (shared_den) { /* one reciprocal for two numerators, as the kernels use it */
+    if (shared_den == 1) { /* one reciprocal for two numerators, as the kernels use it */
         const double y = div_rcp_(b[i]);
         const bool ok = div_in_range_(b[i]);
         const double q1 = div_with_rcp_(a[i], b[i], y, ok), q2 = div_with_rcp_(-a[i], b[i], y, ok);
         o[i] = (q1 == -q2 || (q1 != q1 && q2 != q2)) ? q1 : __longlong_as_double(0x7ff8dead00000000LL);
+    } else if (shared_den >= 2) {
+        /* the step loop's speculative arithmetic (MathFast, ode_device.cuh): the value when the
+         * operands were accepted, a tagged NaN when they were flagged for the exact path */
+        MathFast m;
+        double q;
+        if (shared_den == 2) q = m.div(a[i], b[i]);
+        else if (shared_den == 3) q = m.div_nz(a[i], b[i]);
+        else if (shared_den == 4) q = m.sqrt(a[i]);
+        else if (shared_den == 5) q = m.sqrt_nz(a[i]);
+        else { /* one reciprocal, two numerators */
+            const double rb = m.rcp(b[i]);
+            const double q1 = m.div_by(a[i], b[i], rb), q2 = m.div_by(-a[i], b[i], rb);
+            q = (q1 == -q2 || (q1 != q1 && q2 != q2)) ? q1 : __longlong_as_double(0x7ff8dead00000000LL);
+            if (q1 == 0.0 && (__double2hiint(q1) ^ __double2hiint(q2)) >= 0) q = __longlong_as_double(0x7ff8dead00000000LL);
+        }
+        o[i] = m.bad() ? __longlong_as_double(0x7ff8f1a900000000LL) : q;
     } else {
         o[i] = div_(a[i], b[i]);
     }

@@ -144,6 +144,54 @@ def test_user_system_from_source_matches_builtin_bitwise():
         assert_same_outputs(a, b, "jit vs builtin m%d" % cfg.method)
 
 
+def test_user_system_div_d_sqrt_d_match_plain_operators_and_builtin():
+    """div_d / sqrt_d route a user RHS through the kernels' speculative exact arithmetic (one
+    straight-line block, lockstep CTA for n = 6 Dop853): same bits as `/` and sqrt(), and as the
+    built-in Kepler system"""
+    spec = ("const double r = sqrt_d(y[0] * y[0] + y[1] * y[1] + y[2] * y[2]);\n const double r3 = r * r * r;\n"
+            "dy[0] = y[3]; dy[1] = y[4]; dy[2] = y[5];\n"
+            "dy[3] = div_d(-p[0] * y[0], r3); dy[4] = div_d(-p[0] * y[1], r3); dy[5] = div_d(-p[0] * y[2], r3);")
+    plain = spec.replace("sqrt_d(", "sqrt(").replace("div_d(-p[0] * y[0], r3)", "-p[0] * y[0] / r3").replace(
+        "div_d(-p[0] * y[1], r3)", "-p[0] * y[1] / r3").replace("div_d(-p[0] * y[2], r3)", "-p[0] * y[2] / r3")
+    assert "div_d" not in plain and "sqrt_d" not in plain
+    fs = ob.System.from_source("user_kepler_spec", 6, 1, spec)
+    fp = ob.System.from_source("user_kepler_plain", 6, 1, plain)
+    y0, p = W.kepler_sweep(700, offset=21)
+    for cfg in (ob.config_new(ob.DOP853, 0.0, W.kepler_period(), 60.0, 1e-10, 1e-10, out_type=ob.OUT_SPARSE),
+                ob.config_new(ob.DOPRI5, 0.0, W.kepler_period(), 600.0, 1e-8, 1e-8),
+                ob.config_rk4(0.0, 2000.0, 5.0)):
+        cap = 30 if cfg.out_type == ob.OUT_DENSE and cfg.method != ob.RK4 else 0
+        b = ob.integrate_batch(ob.System.builtin("kepler"), cfg, y0, p, out_cap=cap)
+        for f in (fs, fp):
+            a = ob.integrate_batch(f, cfg, y0, p, out_cap=cap)
+            assert_same_outputs(a, b, "jit kepler m%d" % cfg.method)
+
+
+def test_out_of_window_operands_take_the_exact_path_with_identical_bits():
+    """Kepler in units that push numerators below 2^-969 and reciprocals out of the normal range:
+    the speculative block flags every such attempt and the out-of-line exact recomputation must
+    reproduce the oracle (plain IEEE `/` and sqrt) bit for bit; mixed with ordinary trajectories in the
+    same warps"""
+    n = 512
+    y0, p = W.kepler_sweep(n, offset=3)
+    y0 = y0.copy()
+    p = np.array(p, dtype=np.float64).reshape(1, -1) * np.ones((1, n))
+    # rescale lengths by s and mu by s^3 (same orbits, same periods). s = 1e-76: numerators
+    # mu * y ~ 3e-295 < 2^-969 (normal numbers, but below the fast division's window) for every third
+    # trajectory; s = 1e70 (large but inside the window) for every fifth
+    for sel, s in ((slice(0, n, 3), 1e-76), (slice(1, n, 5), 1e70)):
+        y0[:, sel] *= s
+        p[:, sel] *= s ** 3
+    for cfg in (ob.config_new(ob.DOP853, 0.0, 0.5 * W.kepler_period(), 60.0, 1e-10, 1e-10, out_type=ob.OUT_SPARSE),
+                ob.config_new(ob.DOPRI5, 0.0, 0.25 * W.kepler_period(), 600.0, 1e-8, 1e-10),
+                ob.config_rk4(0.0, 500.0, 5.0)):
+        cap = 30 if cfg.out_type == ob.OUT_DENSE and cfg.method != ob.RK4 else 0
+        g = ob.integrate_batch(ob.System.builtin("kepler"), cfg, y0, p, out_cap=cap)
+        o = oracle.integrate_batch("kepler", cfg, y0, p, out_cap=cap)
+        assert_same_outputs(g, o, "kepler rescaled m%d" % cfg.method)
+        assert int(g.accepted[0::3].min()) > 3
+
+
 def test_user_system_recording_every_step_uses_the_staged_kernels():
     """Sparse / Rk4 recording goes through the STAGE kernel variants (shared-memory runs); the NVRTC
     build of those must match the ahead-of-time one bit for bit"""

@@ -106,3 +106,62 @@ def test_div_matches_ieee():
                        -7.5, 0.9])
         A, B = np.meshgrid(sp, sp)
         assert same_f64(_dev_div(A.ravel(), B.ravel()), A.ravel() / B.ravel()).all()
+
+
+FLAGGED = 0x7ff8f1a900000000
+
+
+def _spec(a, b, mode):
+    out = _dev_div(a, b, shared=mode)
+    flagged = out.view(np.uint64) == FLAGGED
+    return out, flagged
+
+
+def test_speculative_div_and_sqrt_are_ieee_exact_or_flagged():
+    """MathFast (ode_device.cuh): every value the branch-free fast paths return must be the correctly
+    rounded IEEE result; operands they cannot handle must be flagged, never answered wrongly; and
+    ordinary solver magnitudes (and zero numerators) must NOT be flagged, or the step loop would
+    live on its out-of-line exact path"""
+    rng = np.random.default_rng(16)
+    n = 10_000_000
+    with np.errstate(all="ignore"):
+        for rep in range(5):
+            a = np.ldexp(rng.uniform(1, 2, n), rng.integers(-1070, 1023, n)) * rng.choice([-1.0, 1.0], n)
+            b = np.ldexp(rng.uniform(1, 2, n), rng.integers(-1070, 1023, n)) * rng.choice([-1.0, 1.0], n)
+            ordinary = rep >= 2
+            if ordinary:
+                a = rng.standard_normal(n) * 10 ** rng.uniform(-30, 30, n)
+                b = rng.uniform(1e-30, 1e30, n) * rng.choice([-1.0, 1.0], n)
+                a[rng.integers(0, n, n // 10)] = 0.0
+                a[rng.integers(0, n, n // 10)] = -0.0
+            if rep == 4:  # near-ties, mantissas at the ends
+                a = np.ldexp(1 + rng.integers(0, 8, n) * 2.0 ** -52, rng.integers(-300, 300, n))
+                b = np.ldexp(2 - rng.integers(1, 8, n) * 2.0 ** -52, rng.integers(-300, 300, n))
+            for mode in (2, 3, 6):
+                out, fl = _spec(a, b, mode)
+                assert same_f64(out[~fl], (a / b)[~fl]).all(), "mode %d rep %d" % (mode, rep)
+                if ordinary:
+                    nz = a != 0.0
+                    assert not fl[nz].any()
+                    assert fl[~nz].all() if mode == 3 else not fl[~nz].any()
+                else:
+                    assert 0.2 < fl.mean() < 0.9  # the wide exponent sweep leaves the window often
+            x = np.abs(a)
+            for mode in (4, 5):
+                out, fl = _spec(x, x, mode)
+                assert same_f64(out[~fl], np.sqrt(x)[~fl]).all()
+                if ordinary:
+                    nz = x != 0.0
+                    assert not fl[nz].any()
+                    assert fl[~nz].all() if mode == 5 else not fl[~nz].any()
+        sp = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 5e-324, 2.2e-308, 1.7e308, 3.0, 1e-200, 1e200,
+                       -7.5, 0.9, 1e-300, 4e-292, 1e-291, 2.0 ** -970, 2.0 ** -969, 2.0 ** 1016, 2.0 ** 1017])
+        A, B = (v.ravel() for v in np.meshgrid(sp, sp))
+        for mode in (2, 3, 6):
+            out, fl = _spec(A, B, mode)
+            assert same_f64(out[~fl], (A / B)[~fl]).all()
+            assert fl[~np.isfinite(A / B)].all() and fl[~np.isfinite(B)].all()
+        for mode in (4, 5):
+            out, fl = _spec(sp, sp, mode)
+            assert same_f64(out[~fl], np.sqrt(sp)[~fl]).all()
+            assert fl[~(sp >= 0)].all() and fl[np.isinf(sp)].all()
