@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -340,7 +341,8 @@ __global__ void fill_unsupported_kernel(KernelArgs a, int dim) {
 
 /* enqueue the step-loop kernel for device-resident inputs/outputs on `stream` */
 static int launch_device(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg, int64_t n, const double* y0,
-                         const double* params, int per_traj, const ode_b200_outputs* out, cudaStream_t stream) {
+                         const double* params, int per_traj, const ode_b200_outputs* out, long long out_pitch,
+                         cudaStream_t stream) {
     SysInfo s;
     if (!sys_info(sys_id, &s)) return fail(ODE_B200_ERR_UNKNOWN_SYSTEM, "bad sys_id");
     if (int rc = validate(cfg, s, n, y0, params, out)) return rc;
@@ -371,6 +373,7 @@ static int launch_device(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg
     ka.use_queue = c->use_queue;
     ka.queue = c->queue;
     ka.out = *out;
+    ka.out_pitch = out_pitch > 0 ? out_pitch : out->out_cap;
     if (ka.out.out_cap == 0) ka.out.out_x = ka.out.out_y = nullptr;
     if (ka.out.com_cap == 0) ka.out.com_break = ka.out.com_step = ka.out.com_coef = nullptr;
 
@@ -385,16 +388,19 @@ static int launch_device(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg
         return ODE_B200_SUCCESS;
     }
 
-    /* Shared-memory staging of recorded results (ode_kernel_args.h) pays when a lane pushes about
-     * one sample per attempted step or more: every Rk4 step, every accepted step (Sparse /
-     * Continuous), or Dense with many samples per trajectory. Measured on B200 (2^18 Lorenz
-     * trajectories): Rk4 all steps 26.4 -> 12.9 ms, Dense dx=0.01 (2001 samples) 37.4 -> 25.2 ms,
-     * but Dense dx=0.1 (201 samples) 10.9 -> 13.5 ms and CR3BP Dense (41 samples) 55.8 -> 75.9 ms. */
+    /* Staging of recorded results through shared memory and TMA bulk copies (ode_kernel_args.h) pays
+     * when a lane pushes about one sample per attempted step or more: every Rk4 step, every accepted
+     * step (Sparse / Continuous), or Dense with many samples per trajectory; with a few dozen samples
+     * per trajectory the shared memory costs more occupancy than the stores cost time. The bulk copies
+     * need 16-byte aligned rows: an even row pitch and aligned base pointers (always true for the
+     * host-buffer entry, which pads its device rows). */
     bool stage = ka.out.out_x != nullptr;
     if (stage && cfg->method != ODE_B200_RK4 && cfg->out_type == ODE_B200_OUT_DENSE) {
         const double samples = cfg->dx > 0.0 ? fabs(cfg->x_end - cfg->x0) / cfg->dx : 0.0;
         stage = samples >= 1000.0;
     }
+    if (stage && ((ka.out_pitch & 1) != 0 || ((uintptr_t)ka.out.out_x & 15u) != 0 || ((uintptr_t)ka.out.out_y & 15u) != 0))
+        stage = false;
     const size_t dyn_smem = stage ? (size_t)stage_smem_doubles(s.dim, block) * sizeof(double) : 0;
     CUDA_TRY(cudaMemsetAsync(c->queue, 0, sizeof(unsigned long long), stream));
     if (stream == c->stream) CUDA_TRY(cudaEventRecord(c->ev0, stream));
@@ -428,7 +434,7 @@ extern "C" int ode_b200_integrate_batch_device(ode_b200_ctx* c, int sys_id, cons
                                                const ode_b200_outputs* out, void* cuda_stream) {
     if (!c) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
     cudaStream_t st = (cudaStream_t)cuda_stream; /* NULL = the CUDA default stream */
-    return launch_device(c, sys_id, cfg, n, y0, params, per_traj, out, st);
+    return launch_device(c, sys_id, cfg, n, y0, params, per_traj, out, out->out_cap, st);
 }
 
 /* device alias of a pinned, device-mapped host allocation (nullptr for pageable memory) */
@@ -521,10 +527,13 @@ static int integrate_range(ode_b200_ctx* c, int sys_id, const ode_b200_config* c
     WANT_PT(com_count, com_count, 4)
     WANT_PT(com_lower, com_lower, 8)
 #undef WANT_PT
+    /* device rows of the per-step results are padded to a multiple of 4 samples (whole 32-byte
+     * sectors per staged group, 16-byte aligned bulk copies); the copy back strips the padding */
+    const size_t pitch = ((size_t)out->out_cap + 3) & ~(size_t)3;
     if (out->out_cap > 0) {
         dv.out_cap = out->out_cap;
-        WANT(out_x, out_x, (size_t)n * out->out_cap * 8)
-        WANT(out_y, out_y, (size_t)n * out->out_cap * d * 8)
+        WANT(out_x, out_x, (size_t)n * pitch * 8)
+        WANT(out_y, out_y, (size_t)n * pitch * d * 8)
     }
     if (out->com_cap > 0) {
         dv.com_cap = out->com_cap;
@@ -534,7 +543,7 @@ static int integrate_range(ode_b200_ctx* c, int sys_id, const ode_b200_config* c
     }
 #undef WANT
     if (int rc = launch_device(c, sys_id, cfg, n, (const double*)c->y0.p, (const double*)c->params.p, per_traj,
-                               &dv, st))
+                               &dv, (long long)pitch, st))
         return rc;
 
     if (out->y_final && !(zero_copy & 1u))
@@ -564,8 +573,16 @@ static int integrate_range(ode_b200_ctx* c, int sys_id, const ode_b200_config* c
     BACK_PT(com_lower, 8)
 #undef BACK_PT
     if (out->out_cap > 0) {
-        BACK(out_x, 8, (size_t)out->out_cap)
-        BACK(out_y, 8, (size_t)out->out_cap * d)
+        const size_t cap = (size_t)out->out_cap;
+        if (pitch == cap) {
+            BACK(out_x, 8, cap)
+            BACK(out_y, 8, cap * d)
+        } else {
+            CUDA_TRY(cudaMemcpy2DAsync(out->out_x + (size_t)lo * cap, cap * 8, dv.out_x, pitch * 8, cap * 8, (size_t)n,
+                                       cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpy2DAsync(out->out_y + (size_t)lo * cap * d, cap * d * 8, dv.out_y, pitch * d * 8,
+                                       cap * d * 8, (size_t)n, cudaMemcpyDeviceToHost, st));
+        }
     }
     if (out->com_cap > 0) {
         BACK(com_break, 8, (size_t)out->com_cap)

@@ -27,18 +27,22 @@ constexpr int kMaxBlockThreads = 256;
  * Output staging. The per-step results are trajectory-major (one trajectory's samples are
  * contiguous, like the crate's Vec), so a warp whose 32 lanes each push one sample writes 32
  * different 128-byte lines with 8-byte pieces (measured: 0.45-0.64 TB/s of useful writes).
- * Instead every lane collects up to stage_samples(dim) samples in shared memory and the warp
- * writes one lane's run at a time as contiguous 8-byte x 32 stores (full sectors). It costs
- * shared memory (occupancy for n >= 6) and a ballot per pass, so it is a compile-time variant
- * of every kernel (STAGE) that the launcher picks only for output-heavy calls (rule in ode_b200.cu).
- * Lane buffer: x[R] then y[R][dim]; stride is odd so that 32 lanes hit 32 different bank pairs.
+ * In the STAGE variant of every kernel a lane collects its samples in a shared-memory ring of two
+ * groups of stage_group(dim) samples; the moment a group is complete the lane itself hands it to
+ * the TMA engine as two bulk copies (cp.async.bulk.global.shared::cta: the group's x values and its
+ * y vectors, each a contiguous, 16-byte aligned range of the trajectory's slice of out_x / out_y)
+ * and goes on filling the other group -- no store instructions, no warp-level flush in the step
+ * loop. tools/micro/bulk_store.cu: 3.5-4.0 TB/s for this pattern on B200 (32 B + 96 B copies),
+ * 4.3-4.6 TB/s with whole 8-sample runs, against 1.1-1.4 TB/s for per-lane vector stores.
+ * It needs an even row pitch (alignment) and shared memory, so the launcher picks it only for
+ * output-heavy calls (rule in ode_b200.cu). Lane buffer: x[R] then y[R][dim], R = 2 groups.
  */
-__host__ __device__ constexpr int stage_samples(int dim) {
-    return 40 / (1 + dim) < 2 ? 2 : (40 / (1 + dim) > 8 ? 8 : 40 / (1 + dim));
-}
-__host__ __device__ constexpr int stage_stride(int dim) { return (stage_samples(dim) * (1 + dim)) | 1; }
-/* dynamic shared memory of a staging launch: per-thread {staged, base} + the lane buffers */
-__host__ __device__ constexpr int stage_smem_doubles(int dim, int threads) { return threads * (1 + stage_stride(dim)); }
+__host__ __device__ constexpr int stage_group(int dim) { return dim <= 4 ? 4 : 2; }
+__host__ __device__ constexpr int stage_samples(int dim) { return 2 * stage_group(dim); }
+/* in doubles; even (16-byte aligned lane buffers), and not a multiple of 32 (shared-memory banks) */
+__host__ __device__ constexpr int stage_stride(int dim) { return stage_samples(dim) * (1 + dim) + 2; }
+/* dynamic shared memory of a staging launch */
+__host__ __device__ constexpr int stage_smem_doubles(int dim, int threads) { return threads * stage_stride(dim); }
 
 struct KernelArgs {
     ode_b200_config cfg;        /* batch-uniform solver parameters (from_param argument list) */
@@ -58,6 +62,8 @@ struct KernelArgs {
     int use_queue;              /* 1 = persistent lanes refill from *queue; 0 = one thread per trajectory */
     unsigned long long* queue;  /* work-queue head (next unclaimed trajectory index) */
     ode_b200_outputs out;       /* device pointers */
+    long long out_pitch;        /* samples per trajectory row of out_x / out_y in device memory (>= out.out_cap;
+                                   the host-buffer entry pads its rows to a multiple of 4) */
 };
 
 /* the f32 Rk4 kernel's arguments (device pointers) */

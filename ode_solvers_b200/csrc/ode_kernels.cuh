@@ -153,7 +153,7 @@ struct Rk4Stepper {
     /* one Rk4::step + the loop body of integrate, rk4.rs:79-98,103-132 */
     ODE_DEV static bool attempt(State& s, const KernelArgs& a) {
         if (s.steps_left == 0) {
-            store_final_<N>(a, s.traj, s.y, s.x, a.cfg.step_size, s.c, s.status, 0.0);
+            store_final_<N, STAGE>(a, s.traj, s.y, s.x, a.cfg.step_size, s.c, s.status, 0.0);
             return true;
         }
         const double step = a.cfg.step_size, x = s.x;
@@ -190,7 +190,7 @@ struct Rk4Stepper {
         s.steps_left -= 1;
         if (stop) s.steps_left = 0;
         if (s.steps_left == 0) {
-            store_final_<N>(a, s.traj, s.y, s.x, step, s.c, s.status, 0.0);
+            store_final_<N, STAGE>(a, s.traj, s.y, s.x, step, s.c, s.status, 0.0);
             return true;
         }
         return false;
@@ -223,7 +223,7 @@ struct Dopri5Stepper {
     };
 
     ODE_DEV static bool finish(State& s, const KernelArgs& a, int status) {
-        store_final_<N>(a, s.traj, s.y, s.x, s.h_old, s.c, status, a.cfg.x0);
+        store_final_<N, STAGE>(a, s.traj, s.y, s.x, s.h_old, s.c, status, a.cfg.x0);
         return true;
     }
 
@@ -524,7 +524,7 @@ struct Dop853Stepper {
     };
 
     ODE_DEV static bool finish(State& s, const KernelArgs& a, int status) {
-        store_final_<N>(a, s.traj, s.y, s.x, s.h_old, s.c, status, CONT8 ? a.cfg.x0 : 0.0);
+        store_final_<N, STAGE>(a, s.traj, s.y, s.x, s.h_old, s.c, status, CONT8 ? a.cfg.x0 : 0.0);
         return true;
     }
 
