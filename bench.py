@@ -153,6 +153,53 @@ class ClockSampler:
                 "samples_in_region": len(sm), "reasons": sorted(reasons)}
 
 
+# ---------------------------------------------------------------- the other configs (GPU)
+def other_workloads(ob, W, ctx, peak_inst):
+    """Kernel time (CUDA events inside the library, best of 2 after one warm-up) of the other
+    BASELINE.json configs through the host-buffer entry: steps/s, nominal algorithmic TFLOP/s as a
+    fraction of the unfused FP64 peak (flop formulas: BASELINE.md section 2), and GB/s of recorded
+    samples for the output-heavy runs. Parity of every one of these kernels is a tests/ matter."""
+    per = W.kepler_period()
+    cases = [
+        ("configs[1] Lorenz 2^20, Rk4 h=1e-3 (20000 steps each), final state", "lorenz", W.lorenz_ensemble, 1 << 20,
+         ob.config_rk4(0.0, 20.0, 1e-3), 0, 13 * 3 + 4 * 8 + 4),
+        ("configs[1] Lorenz 2^20, Dop853 1e-6", "lorenz", W.lorenz_ensemble, 1 << 20,
+         ob.config_new(ob.DOP853, 0.0, 20.0, 0.1, 1e-6, 1e-6, out_type=ob.OUT_SPARSE), 0, 146 * 3 + 11 * 8 + 90),
+        ("configs[2] Kepler e-sweep 2^22 (4M), Dop853 1e-10, 5 periods", "kepler", W.kepler_sweep, 1 << 22,
+         ob.config_new(ob.DOP853, 0.0, 5.0 * per, 60.0, 1e-10, 1e-10, out_type=ob.OUT_SPARSE), 0, 146 * 6 + 11 * 14 + 90),
+        ("configs[3] CR3BP 2^18, Dop853 1e-12, Dense dx=0.5", "cr3bp", W.cr3bp_ensemble, 1 << 18,
+         ob.config_new(ob.DOP853, 0.0, 20.0, 0.5, 1e-12, 1e-12), 43, 146 * 6 + 11 * 39 + 90),
+        ("configs[3] Newtonian 3-body SVector<f64,18> 2^18, Dop853 1e-9", "threebody18", W.threebody18_ensemble, 1 << 18,
+         ob.config_new(ob.DOP853, 0.0, 5.0, 0.1, 1e-9, 1e-9, out_type=ob.OUT_SPARSE), 0, 146 * 18 + 11 * 90 + 90),
+        ("configs[4] Robertson rate sweep 2^20, Dop853 rtol=1e-2 atol=1e-6", "robertson", W.robertson_sweep, 1 << 20,
+         ob.config_new(ob.DOP853, 0.0, 0.3, 0.3, 1e-2, 1e-6, out_type=ob.OUT_SPARSE), 0, 146 * 3 + 11 * 10 + 90),
+        ("output-heavy: Lorenz 2^17, Rk4 h=1e-3 0->2, every step recorded (2001 x 32 B each)", "lorenz",
+         W.lorenz_ensemble, 1 << 17, ob.config_rk4(0.0, 2.0, 1e-3), 2004, 13 * 3 + 4 * 8 + 4),
+        ("output-heavy: Lorenz 2^17, Dopri5 1e-6 Dense dx=0.01 (2001 samples each)", "lorenz", W.lorenz_ensemble,
+         1 << 17, ob.config_new(ob.DOPRI5, 0.0, 20.0, 0.01, 1e-6, 1e-6), 2004, 63 * 3 + 6 * 8 + 25 + 12 * 3),
+    ]
+    rows = []
+    for label, sysname, gen, n, cfg, cap, flops in cases:
+        y0, p = gen(n)
+        f = ob.System.builtin(sysname)
+        best = None
+        for _ in range(2 if cap else 3):
+            o = ob.integrate_batch(f, cfg, y0, p, out_cap=cap, ctx=ctx)
+            best = o.kernel_ms if best is None else min(best, o.kernel_ms)
+        acc, att = int(o.accepted.sum()), int(o.n_step.sum())
+        row = {"workload": label, "trajectories": n, "kernel_ms": round(best, 3),
+               "accepted_steps_per_s": acc / (best * 1e-3), "attempted_steps": att,
+               "algorithmic_tflops": flops * att / (best * 1e-3) / 1e12,
+               "unfused_frac": flops * att / (best * 1e-3) / peak_inst, "trajectories_not_ok": int((o.status != 0).sum())}
+        if cap:
+            stored = int(np.minimum(o.out_count, cap).sum()) * (1 + y0.shape[0]) * 8
+            row["sample_bytes"] = stored
+            row["sample_write_gbs"] = stored / (best * 1e-3) / 1e9
+        rows.append(row)
+        del o
+    return rows
+
+
 # ---------------------------------------------------------------- native arm (GPU)
 def run_native(args):
     import torch
@@ -319,6 +366,11 @@ def run_native(args):
                "sample": "first %d of %d trajectories, %.1f s, OpenMP schedule(dynamic) over trajectories" % (
                    ns, n, dt)}
 
+    # ---- the other BASELINE.json configs on the same kernels (N = 1 only; reported, not the metric)
+    others = None
+    if world == 1 and not args.no_extra:
+        others = other_workloads(ob, workloads, ctx, peak_inst)
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -331,6 +383,7 @@ def run_native(args):
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "other_workloads": others,
         "accepted_steps_per_pass": tot_acc, "attempted_steps_per_pass": tot_att,
         "trajectories_not_ok": n_bad,
         "step_ms": [round(v, 4) for v in step_ms],
@@ -364,6 +417,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other_workloads leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -432,10 +432,14 @@ struct Dopri5Stepper {
             if constexpr (DENSE) {
                 bool unsupported = false;
                 double yo[N];
+                /* every sample of this step divides by the same h_old: one refined reciprocal, exact
+                 * quotients (div_with_rcp_, ode_device.cuh) */
+                const double rh = div_rcp_(s.h_old);
+                const bool h_ok = div_in_range_(s.h_old);
                 while (fabs(s.xd) <= fabs(s.x)) {
                     bool pushed = false;
                     if (fabs(s.x_old) <= fabs(s.xd) && fabs(s.x) >= fabs(s.xd)) {
-                        const double th = (s.xd - s.x_old) / s.h_old, th1 = 1.0 - th;
+                        const double th = div_with_rcp_(s.xd - s.x_old, s.h_old, rh, h_ok), th1 = 1.0 - th;
                         y_out(rc, th, th1, yo);
                         push_<N, STAGE>(a, s.traj, s.c, s.xd, yo);
                         if constexpr (TRACK_LAST) {
@@ -455,7 +459,7 @@ struct Dopri5Stepper {
                 }
                 if (unsupported) return finish(s, a, ODE_B200_UNSUPPORTED_DOMAIN);
                 if (fabs(s.xd - cfg.x_end) < 1.0e-9) { /* endpoint rule, dopri5.rs:472-478 (Q9) */
-                    const double th = (cfg.x_end - s.x_old) / s.h_old, th1 = 1.0 - th;
+                    const double th = div_with_rcp_(cfg.x_end - s.x_old, s.h_old, rh, h_ok), th1 = 1.0 - th;
                     y_out(rc, th, th1, yo);
                     push_<N, STAGE>(a, s.traj, s.c, cfg.x_end, yo);
                     if constexpr (TRACK_LAST) {
@@ -832,9 +836,11 @@ struct Dop853Stepper {
                     s.xd += cfg.dx;
                 } else {
                     bool unsupported = false;
+                    const double rh = div_rcp_(s.h_old); /* one reciprocal for every sample of the step */
+                    const bool h_ok = div_in_range_(s.h_old);
                     while (fabs(s.xd) <= fabs(s.x)) {
                         if (fabs(s.x_old) <= fabs(s.xd) && fabs(s.x) >= fabs(s.xd)) {
-                            const double th = (s.xd - s.x_old) / s.h_old, th1 = 1.0 - th;
+                            const double th = div_with_rcp_(s.xd - s.x_old, s.h_old, rh, h_ok), th1 = 1.0 - th;
                             y_out(rc, th, th1, yo);
                             push_<N, STAGE>(a, s.traj, s.c, s.xd, yo);
                             if constexpr (TRACK_LAST) {
@@ -850,7 +856,7 @@ struct Dop853Stepper {
                     }
                     if (unsupported) return finish(s, a, ODE_B200_UNSUPPORTED_DOMAIN);
                     if (fabs(s.xd - cfg.x_end) < 1.0e-9) {
-                        const double th = (cfg.x_end - s.x_old) / s.h_old, th1 = 1.0 - th;
+                        const double th = div_with_rcp_(cfg.x_end - s.x_old, s.h_old, rh, h_ok), th1 = 1.0 - th;
                         y_out(rc, th, th1, yo);
                         push_<N, STAGE>(a, s.traj, s.c, cfg.x_end, yo);
                         if constexpr (TRACK_LAST) {
