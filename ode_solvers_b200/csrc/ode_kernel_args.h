@@ -20,7 +20,12 @@ __host__ __device__ constexpr bool lockstep_for(int dim, int method) {
     return dim > 8 || (dim >= 6 && method == ODE_B200_DOP853);
 #endif
 }
-__host__ __device__ constexpr int block_threads_for(int dim, int method) { return lockstep_for(dim, method) ? 256 : 128; }
+#ifndef ODE_B200_BIG_THREADS
+#define ODE_B200_BIG_THREADS 256
+#endif
+__host__ __device__ constexpr int block_threads_for(int dim, int method) {
+    return lockstep_for(dim, method) ? (dim > 8 ? ODE_B200_BIG_THREADS : 256) : 128;
+}
 constexpr int kMaxBlockThreads = 256;
 
 /*
