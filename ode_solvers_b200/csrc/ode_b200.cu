@@ -343,7 +343,7 @@ __global__ void fill_unsupported_kernel(KernelArgs a, int dim) {
 /* enqueue the step-loop kernel for device-resident inputs/outputs on `stream` */
 static int launch_device(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg, int64_t n, const double* y0,
                          const double* params, int per_traj, const ode_b200_outputs* out, long long out_pitch,
-                         cudaStream_t stream) {
+                         long long com_pitch, cudaStream_t stream) {
     SysInfo s;
     if (!sys_info(sys_id, &s)) return fail(ODE_B200_ERR_UNKNOWN_SYSTEM, "bad sys_id");
     if (int rc = validate(cfg, s, n, y0, params, out)) return rc;
@@ -375,6 +375,7 @@ static int launch_device(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg
     ka.queue = c->queue;
     ka.out = *out;
     ka.out_pitch = out_pitch > 0 ? out_pitch : out->out_cap;
+    ka.com_pitch = com_pitch > 0 ? com_pitch : out->com_cap;
     if (ka.out.out_cap == 0) ka.out.out_x = ka.out.out_y = nullptr;
     if (ka.out.com_cap == 0) ka.out.com_break = ka.out.com_step = ka.out.com_coef = nullptr;
 
@@ -403,12 +404,21 @@ static int launch_device(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg
     }
     if (stage && ((ka.out_pitch & 1) != 0 || ((uintptr_t)ka.out.out_x & 15u) != 0 || ((uintptr_t)ka.out.out_y & 15u) != 0))
         stage = false;
-    const size_t dyn_smem = stage ? (size_t)stage_smem_doubles(s.dim, block) * sizeof(double) : 0;
+    /* coefficient vectors per interval of the continuous output model this call records (0: none) */
+    const int com_m = ka.out.com_break == nullptr ? 0
+                      : (cfg->method == ODE_B200_DOPRI5 && cfg->out_type == ODE_B200_OUT_CONTINUOUS)   ? 5
+                      : (cfg->method == ODE_B200_DOP853 && cfg->out_type == ODE_B200_OUT_CONTINUOUS8) ? 8
+                                                                                                      : 0;
+    if (stage && com_m > 0 &&
+        ((ka.com_pitch & 1) != 0 || ((uintptr_t)ka.out.com_break & 15u) != 0 || ((uintptr_t)ka.out.com_step & 15u) != 0 ||
+         ((uintptr_t)ka.out.com_coef & 15u) != 0))
+        stage = false;
+    const size_t dyn_smem = stage ? (size_t)stage_smem_doubles(s.dim, block, com_m) * sizeof(double) : 0;
     CUDA_TRY(cudaMemsetAsync(c->queue, 0, sizeof(unsigned long long), stream));
     if (stream == c->stream) CUDA_TRY(cudaEventRecord(c->ev0, stream));
     if (!s.jit) {
         const void* fn = kBuiltins[sys_id]->kernels[stage ? 1 : 0][cfg->method][cfg->out_type];
-        if (dyn_smem > 48 * 1024)
+        if (dyn_smem > 32 * 1024) /* static tables + dynamic rings may exceed the 48 KB default together */
             CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
         int per_sm = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block, dyn_smem));
@@ -436,7 +446,7 @@ extern "C" int ode_b200_integrate_batch_device(ode_b200_ctx* c, int sys_id, cons
                                                const ode_b200_outputs* out, void* cuda_stream) {
     if (!c) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
     cudaStream_t st = (cudaStream_t)cuda_stream; /* NULL = the CUDA default stream */
-    return launch_device(c, sys_id, cfg, n, y0, params, per_traj, out, out->out_cap, st);
+    return launch_device(c, sys_id, cfg, n, y0, params, per_traj, out, out->out_cap, out->com_cap, st);
 }
 
 /* device alias of a pinned, device-mapped host allocation (nullptr for pageable memory) */
@@ -537,15 +547,16 @@ static int integrate_range(ode_b200_ctx* c, int sys_id, const ode_b200_config* c
         WANT(out_x, out_x, (size_t)n * pitch * 8)
         WANT(out_y, out_y, (size_t)n * pitch * d * 8)
     }
+    const size_t cpitch = ((size_t)out->com_cap + 3) & ~(size_t)3;
     if (out->com_cap > 0) {
         dv.com_cap = out->com_cap;
-        WANT(com_break, com_break, (size_t)n * out->com_cap * 8)
-        WANT(com_step, com_step, (size_t)n * out->com_cap * 8)
-        WANT(com_coef, com_coef, (size_t)n * out->com_cap * m * d * 8)
+        WANT(com_break, com_break, (size_t)n * cpitch * 8)
+        WANT(com_step, com_step, (size_t)n * cpitch * 8)
+        WANT(com_coef, com_coef, (size_t)n * cpitch * m * d * 8)
     }
 #undef WANT
     if (int rc = launch_device(c, sys_id, cfg, n, (const double*)c->y0.p, (const double*)c->params.p, per_traj,
-                               &dv, (long long)pitch, st))
+                               &dv, (long long)pitch, (long long)cpitch, st))
         return rc;
 
     if (out->y_final && !(zero_copy & 1u))
@@ -587,9 +598,19 @@ static int integrate_range(ode_b200_ctx* c, int sys_id, const ode_b200_config* c
         }
     }
     if (out->com_cap > 0) {
-        BACK(com_break, 8, (size_t)out->com_cap)
-        BACK(com_step, 8, (size_t)out->com_cap)
-        BACK(com_coef, 8, (size_t)out->com_cap * m * d)
+        const size_t cap = (size_t)out->com_cap;
+        if (cpitch == cap) {
+            BACK(com_break, 8, cap)
+            BACK(com_step, 8, cap)
+            BACK(com_coef, 8, cap * m * d)
+        } else {
+            CUDA_TRY(cudaMemcpy2DAsync(out->com_break + (size_t)lo * cap, cap * 8, dv.com_break, cpitch * 8, cap * 8,
+                                       (size_t)n, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpy2DAsync(out->com_step + (size_t)lo * cap, cap * 8, dv.com_step, cpitch * 8, cap * 8,
+                                       (size_t)n, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpy2DAsync(out->com_coef + (size_t)lo * cap * m * d, cap * m * d * 8, dv.com_coef,
+                                       cpitch * m * d * 8, cap * m * d * 8, (size_t)n, cudaMemcpyDeviceToHost, st));
+        }
     }
 #undef BACK
     CUDA_TRY(cudaStreamSynchronize(st));

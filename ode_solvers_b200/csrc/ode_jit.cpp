@@ -289,7 +289,7 @@ bool jit_launch(int idx, int device, int num_sms, int method, int out_type, bool
             c = it->second;
         }
     }
-    if (dyn_smem > 48 * 1024) a.FuncSetAttribute(c.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)dyn_smem);
+    if (dyn_smem > 32 * 1024) a.FuncSetAttribute(c.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)dyn_smem);
     int per_sm = 0;
     if (a.Occupancy(&per_sm, c.fn, block, dyn_smem) != CUDA_SUCCESS || per_sm < 1) {
         *err = "JIT kernel does not fit on an SM";

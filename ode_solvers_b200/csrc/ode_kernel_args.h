@@ -14,7 +14,9 @@ namespace ode_b200 {
  * CR3BP/Dop853/Dense 50.7 ms (4 x 128 threads) -> 38.4 (1 x 256) -> 33.5 (lockstep);
  * 3-body-18/Dop853 22.5 -> 16.8 -> 12.5. -DODE_B200_LOCKSTEP=0/1 forces it for measurements. */
 __host__ __device__ constexpr bool lockstep_for(int dim, int method) {
-#ifdef ODE_B200_LOCKSTEP
+#ifdef ODE_B200_LOCKSTEP_ALL6
+    return dim >= 6 && method != ODE_B200_RK4;
+#elif defined(ODE_B200_LOCKSTEP)
     return ODE_B200_LOCKSTEP != 0 && (dim > 8 || (dim >= 6 && method == ODE_B200_DOP853));
 #else
     return dim > 8 || (dim >= 6 && method == ODE_B200_DOP853);
@@ -46,8 +48,17 @@ __host__ __device__ constexpr int stage_group(int dim) { return dim <= 4 ? 4 : 2
 __host__ __device__ constexpr int stage_samples(int dim) { return 2 * stage_group(dim); }
 /* in doubles; even (16-byte aligned lane buffers), and not a multiple of 32 (shared-memory banks) */
 __host__ __device__ constexpr int stage_stride(int dim) { return stage_samples(dim) * (1 + dim) + 2; }
-/* dynamic shared memory of a staging launch */
-__host__ __device__ constexpr int stage_smem_doubles(int dim, int threads) { return threads * stage_stride(dim); }
+/* ContinuousOutputModel intervals (breakpoint, step size, m coefficient vectors) are staged the same
+ * way when they fit: a ring of two groups of 2 intervals per lane -- break[4], step[4], coef[4][m][dim]
+ * -- each group leaving as three bulk copies. 0 = written directly (large dim * m). */
+__host__ __device__ constexpr int com_stage_stride(int dim, int m, int threads) {
+    return (stage_stride(dim) + 4 * (2 + m * dim)) * threads * 8 <= 110 * 1024 ? 4 * (2 + m * dim) : 0;
+}
+/* dynamic shared memory of a staging launch; m = coefficient vectors per interval of the call's
+ * continuous output model (0: none recorded) */
+__host__ __device__ constexpr int stage_smem_doubles(int dim, int threads, int m) {
+    return threads * (stage_stride(dim) + (m > 0 ? com_stage_stride(dim, m, threads) : 0));
+}
 
 struct KernelArgs {
     ode_b200_config cfg;        /* batch-uniform solver parameters (from_param argument list) */
@@ -67,6 +78,7 @@ struct KernelArgs {
     int use_queue;              /* 1 = persistent lanes refill from *queue; 0 = one thread per trajectory */
     unsigned long long* queue;  /* work-queue head (next unclaimed trajectory index) */
     ode_b200_outputs out;       /* device pointers */
+    long long com_pitch;        /* intervals per trajectory row of com_break / com_step / com_coef (>= out.com_cap) */
     long long out_pitch;        /* samples per trajectory row of out_x / out_y in device memory (>= out.out_cap;
                                    the host-buffer entry pads its rows to a multiple of 4) */
 };

@@ -207,6 +207,8 @@ struct Dopri5Stepper {
     static constexpr bool TRACK_LAST = DENSE && Sys::HAS_SOLOUT;
     static constexpr int kMinBlocks = min_blocks_for<N, ODE_B200_DOPRI5, DENSE || CONT>();
     static constexpr bool kSpec = spec_math_for<Sys, ODE_B200_DOPRI5>();
+    /* shared-memory ring of ContinuousOutputModel intervals (0: written directly) */
+    static constexpr int kCS = (STAGE && CONT) ? com_stage_stride(N, 5, block_threads_for(N, ODE_B200_DOPRI5)) : 0;
     static constexpr bool kLockstep = lockstep_for(N, ODE_B200_DOPRI5);
     static constexpr int kThreads = block_threads_for(N, ODE_B200_DOPRI5);
     static constexpr int kRefillIdle = kLockstep ? ODE_B200_REFILL_IDLE : ODE_B200_REFILL_IDLE_FREE;
@@ -223,7 +225,7 @@ struct Dopri5Stepper {
     };
 
     ODE_DEV static bool finish(State& s, const KernelArgs& a, int status) {
-        store_final_<N, STAGE>(a, s.traj, s.y, s.x, s.h_old, s.c, status, a.cfg.x0);
+        store_final_<N, STAGE, 5, kCS>(a, s.traj, s.y, s.x, s.h_old, s.c, status, a.cfg.x0);
         return true;
     }
 
@@ -241,7 +243,7 @@ struct Dopri5Stepper {
             s.c.num_eval += 2;
         }
         s.h_old = s.h;
-        if constexpr (OUT == ODE_B200_OUT_SPARSE) push_<N, STAGE>(a, t, s.c, s.x, s.y);
+        if constexpr (OUT == ODE_B200_OUT_SPARSE) push_<N, STAGE, kCS>(a, t, s.c, s.x, s.y);
         rhs_checked_<Sys>(s.x, s.y, s.k0, s.p);
         s.c.num_eval += 1;
     }
@@ -441,7 +443,7 @@ struct Dopri5Stepper {
                     if (fabs(s.x_old) <= fabs(s.xd) && fabs(s.x) >= fabs(s.xd)) {
                         const double th = div_with_rcp_(s.xd - s.x_old, s.h_old, rh, h_ok), th1 = 1.0 - th;
                         y_out(rc, th, th1, yo);
-                        push_<N, STAGE>(a, s.traj, s.c, s.xd, yo);
+                        push_<N, STAGE, kCS>(a, s.traj, s.c, s.xd, yo);
                         if constexpr (TRACK_LAST) {
 #pragma unroll
                             for (int i = 0; i < N; ++i) s.ylast[i] = yo[i];
@@ -461,7 +463,7 @@ struct Dopri5Stepper {
                 if (fabs(s.xd - cfg.x_end) < 1.0e-9) { /* endpoint rule, dopri5.rs:472-478 (Q9) */
                     const double th = div_with_rcp_(cfg.x_end - s.x_old, s.h_old, rh, h_ok), th1 = 1.0 - th;
                     y_out(rc, th, th1, yo);
-                    push_<N, STAGE>(a, s.traj, s.c, cfg.x_end, yo);
+                    push_<N, STAGE, kCS>(a, s.traj, s.c, cfg.x_end, yo);
                     if constexpr (TRACK_LAST) {
 #pragma unroll
                         for (int i = 0; i < N; ++i) s.ylast[i] = yo[i];
@@ -471,20 +473,9 @@ struct Dopri5Stepper {
                 if (s.c.out_count == 0) return finish(s, a, ODE_B200_UNSUPPORTED_DOMAIN);
                 if constexpr (Sys::HAS_SOLOUT) stop = Sys::solout(s.x, s.ylast, s.k0, s.p);
             } else {
-                push_<N, STAGE>(a, s.traj, s.c, s.x, s.y);
-                if constexpr (CONT) { /* add_interval(|x|, rcont, h_old), dopri5.rs:484-486 */
-                    const ode_b200_outputs& o = a.out;
-                    if (o.com_break != nullptr && (long long)s.c.com_count < o.com_cap) {
-                        const size_t q = (size_t)s.traj * (size_t)o.com_cap + s.c.com_count;
-                        o.com_break[q] = fabs(s.x);
-                        o.com_step[q] = s.h_old;
-#pragma unroll
-                        for (int r = 0; r < 5; ++r)
-#pragma unroll
-                            for (int i = 0; i < N; ++i) o.com_coef[(q * 5 + r) * N + i] = rc[r][i];
-                    }
-                    s.c.com_count += 1;
-                }
+                push_<N, STAGE, kCS>(a, s.traj, s.c, s.x, s.y);
+                if constexpr (CONT) /* add_interval(|x|, rcont, h_old), dopri5.rs:484-486 */
+                    push_com_<N, 5, kCS>(a, s.traj, s.c, fabs(s.x), s.h_old, rc);
                 if constexpr (Sys::HAS_SOLOUT) stop = Sys::solout(s.x, s.y, s.k0, s.p);
             }
             if (stop) last = true;
@@ -512,6 +503,7 @@ struct Dop853Stepper {
     static constexpr bool TRACK_LAST = DENSE && Sys::HAS_SOLOUT;
     static constexpr int kMinBlocks = min_blocks_for<N, ODE_B200_DOP853, DENSE || CONT8>();
     static constexpr bool kSpec = spec_math_for<Sys, ODE_B200_DOP853>();
+    static constexpr int kCS = (STAGE && CONT8) ? com_stage_stride(N, 8, block_threads_for(N, ODE_B200_DOP853)) : 0;
     static constexpr bool kLockstep = lockstep_for(N, ODE_B200_DOP853);
     static constexpr int kThreads = block_threads_for(N, ODE_B200_DOP853);
     static constexpr int kRefillIdle = kLockstep ? ODE_B200_REFILL_IDLE : ODE_B200_REFILL_IDLE_FREE;
@@ -528,7 +520,7 @@ struct Dop853Stepper {
     };
 
     ODE_DEV static bool finish(State& s, const KernelArgs& a, int status) {
-        store_final_<N, STAGE>(a, s.traj, s.y, s.x, s.h_old, s.c, status, CONT8 ? a.cfg.x0 : 0.0);
+        store_final_<N, STAGE, 8, kCS>(a, s.traj, s.y, s.x, s.h_old, s.c, status, CONT8 ? a.cfg.x0 : 0.0);
         return true;
     }
 
@@ -561,14 +553,14 @@ struct Dop853Stepper {
         /* solution_output(y0), dop853.rs:273-274 -> :515-519 / :541 */
         if constexpr (DENSE) {
             /* first call: |xd - x0| = 0 < EPSILON always */
-            push_<N, STAGE>(a, t, s.c, a.cfg.x0, s.y);
+            push_<N, STAGE, kCS>(a, t, s.c, a.cfg.x0, s.y);
             if constexpr (TRACK_LAST) {
 #pragma unroll
                 for (int i = 0; i < N; ++i) s.ylast[i] = s.y[i];
             }
             s.xd += a.cfg.dx;
         } else {
-            push_<N, STAGE>(a, t, s.c, a.cfg.x0, s.y);
+            push_<N, STAGE, kCS>(a, t, s.c, a.cfg.x0, s.y);
         }
         rhs_checked_<Sys>(s.x, s.y, s.k0, s.p);
         s.c.num_eval += 1;
@@ -828,7 +820,7 @@ struct Dop853Stepper {
             if constexpr (DENSE) {
                 double yo[N];
                 if (fabs(s.xd - cfg.x0) < 2.220446049250313e-16) {
-                    push_<N, STAGE>(a, s.traj, s.c, cfg.x0, s.y);
+                    push_<N, STAGE, kCS>(a, s.traj, s.c, cfg.x0, s.y);
                     if constexpr (TRACK_LAST) {
 #pragma unroll
                         for (int i = 0; i < N; ++i) s.ylast[i] = s.y[i];
@@ -842,7 +834,7 @@ struct Dop853Stepper {
                         if (fabs(s.x_old) <= fabs(s.xd) && fabs(s.x) >= fabs(s.xd)) {
                             const double th = div_with_rcp_(s.xd - s.x_old, s.h_old, rh, h_ok), th1 = 1.0 - th;
                             y_out(rc, th, th1, yo);
-                            push_<N, STAGE>(a, s.traj, s.c, s.xd, yo);
+                            push_<N, STAGE, kCS>(a, s.traj, s.c, s.xd, yo);
                             if constexpr (TRACK_LAST) {
 #pragma unroll
                                 for (int i = 0; i < N; ++i) s.ylast[i] = yo[i];
@@ -858,7 +850,7 @@ struct Dop853Stepper {
                     if (fabs(s.xd - cfg.x_end) < 1.0e-9) {
                         const double th = div_with_rcp_(cfg.x_end - s.x_old, s.h_old, rh, h_ok), th1 = 1.0 - th;
                         y_out(rc, th, th1, yo);
-                        push_<N, STAGE>(a, s.traj, s.c, cfg.x_end, yo);
+                        push_<N, STAGE, kCS>(a, s.traj, s.c, cfg.x_end, yo);
                         if constexpr (TRACK_LAST) {
 #pragma unroll
                             for (int i = 0; i < N; ++i) s.ylast[i] = yo[i];
@@ -869,20 +861,10 @@ struct Dop853Stepper {
             } else if constexpr (CONT8) {
                 /* extension: (x, y) like Dopri5's Continuous push (dopri5.rs:479-481) and
                  * add_interval(|x|, rcont[0..7], h_old) like dopri5.rs:484-486 */
-                push_<N, STAGE>(a, s.traj, s.c, s.x, s.y);
-                const ode_b200_outputs& o = a.out;
-                if (o.com_break != nullptr && (long long)s.c.com_count < o.com_cap) {
-                    const size_t q = (size_t)s.traj * (size_t)o.com_cap + s.c.com_count;
-                    o.com_break[q] = fabs(s.x);
-                    o.com_step[q] = s.h_old;
-#pragma unroll
-                    for (int r = 0; r < 8; ++r)
-#pragma unroll
-                        for (int i = 0; i < N; ++i) o.com_coef[(q * 8 + r) * N + i] = rc[r][i];
-                }
-                s.c.com_count += 1;
+                push_<N, STAGE, kCS>(a, s.traj, s.c, s.x, s.y);
+                push_com_<N, 8, kCS>(a, s.traj, s.c, fabs(s.x), s.h_old, rc);
             } else {
-                push_<N, STAGE>(a, s.traj, s.c, cfg.x0, s.y); /* pushes x0, not x (Q6) */
+                push_<N, STAGE, kCS>(a, s.traj, s.c, cfg.x0, s.y); /* pushes x0, not x (Q6) */
             }
 
             bool stop = false;
