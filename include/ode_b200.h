@@ -164,6 +164,12 @@ const char* ode_b200_system_name(int sys_id);
  *   __device__ void rhs(double x, const double* y, double* dy, const double* p)
  * and solout_body (NULL = never stop) the body of
  *   __device__ bool solout(double x, const double* y, const double* dy, const double* p)
+ * rhs must write every component of dy. Inside rhs_body, `pow_d(x, y)` and `exp_d(x)` are the
+ * host-libm-identical f64::powf / f64::exp; `div_d(a, b)` and `sqrt_d(x)` are `a / b` and `sqrt(x)`
+ * (same correctly rounded results) routed through the step loop's branch-free speculative arithmetic,
+ * which lets the kernel evaluate a whole attempted step as one straight-line block -- recommended for
+ * right-hand sides that divide or take roots (the built-in Kepler / CR3BP / 3-body systems use it);
+ * the plain operators stay valid.
  * Returns sys_id >= 0 or a negative error (compile log in ode_b200_last_error()).
  */
 int ode_b200_system_from_source(const char* name, int dim, int n_params,

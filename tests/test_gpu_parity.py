@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 import ode_solvers_b200 as ob
+import oracle
 from ode_solvers_b200 import workloads as W
 from parity_util import ENSEMBLES, assert_same_outputs, run_both
 
@@ -87,6 +88,37 @@ def test_per_trajectory_params_and_odd_sizes():
         cfg = ob.config_new(ob.DOPRI5, 0.0, 0.3, 0.3, 1e-2, 1e-6, out_type=ob.OUT_SPARSE)
         g, o = run_both("robertson", cfg, y0, k)
         assert_same_outputs(g, o, "robertson n=%d" % n)
+
+
+@pytest.mark.parametrize("n", [1, 31, 255, 257, 600])
+def test_lockstep_ctas_with_odd_sizes_and_both_schedules(n):
+    """Dop853 with n >= 6 runs one 256-thread lockstep CTA per SM with batched refills: partial CTAs,
+    a single trajectory, more trajectories than lanes per CTA, with and without the work queue"""
+    y0, p = W.kepler_sweep(n, offset=40 + n)
+    cfg = ob.config_new(ob.DOP853, 0.0, 0.7 * W.kepler_period(), 60.0, 1e-9, 1e-9, out_type=ob.OUT_SPARSE)
+    o = oracle.integrate_batch("kepler", cfg, y0, p, out_cap=300)
+    ctx = ob.Context(0)
+    for queue in (True, False):
+        ctx.set_work_queue(queue)
+        g = ob.integrate_batch(ob.System.builtin("kepler"), cfg, y0, p, out_cap=300, ctx=ctx)
+        assert_same_outputs(g, o, "kepler lockstep n=%d queue=%d" % (n, queue))
+    ctx.close()
+
+
+def test_work_queue_refills_lockstep_ctas_many_times():
+    """far more trajectories than resident lanes (148 SMs x 256), very different lengths: every lane
+    refills several times, in batches"""
+    n = 148 * 256 * 3 + 77
+    y0, p = W.kepler_sweep(n, offset=5)
+    cfg = ob.config_new(ob.DOP853, 0.0, 0.25 * W.kepler_period(), 60.0, 1e-7, 1e-7, out_type=ob.OUT_SPARSE)
+    g = ob.integrate_batch(ob.System.builtin("kepler"), cfg, y0, p)
+    assert (g.status == ob.OK).all() and (g.x_final == cfg.x_end).all()
+    sel = np.concatenate([np.arange(0, 300), np.arange(n - 300, n), np.arange(0, n, 997)])
+    o = oracle.integrate_batch("kepler", cfg, y0[:, sel], p)
+    for k in ("accepted", "rejected", "num_eval", "n_step"):
+        assert (getattr(g, k)[sel] == getattr(o, k)).all(), k
+    assert (g.y_final[:, sel].view(np.uint64) == o.y_final.view(np.uint64)).all()
+    assert (g.h_next[sel].view(np.uint64) == o.h_next.view(np.uint64)).all()
 
 
 def test_empty_batch():
