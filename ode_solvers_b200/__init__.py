@@ -5,8 +5,8 @@ from . import _abi, workloads  # noqa: F401
 from ._abi import (DOP853, DOPRI5, RK4, OUT_CONTINUOUS, OUT_CONTINUOUS8, OUT_DENSE, OUT_SPARSE,  # noqa: F401
                    OK, MAX_NUM_STEP_REACHED, STEP_SIZE_UNDERFLOW, STIFFNESS_DETECTED,
                    OUTPUT_CAPACITY_EXCEEDED, UNSUPPORTED_DOMAIN)
-from .api import (Context, ContinuousOutputModel, Dop853, Dopri5, IntegrationError,  # noqa: F401
+from .api import (Context, ContinuousOutputModel, Dop853, Dopri5, DynSystem, IntegrationError,  # noqa: F401
                   MaxNumStepReached, Ode200Error, OutputType, Rk4, SolverResult, Stats,
                   StepSizeUnderflow, StiffnessDetected, System, UnsupportedDomain, com_evaluate_batch,
                   config_from_param, config_new, config_rk4, default_context, device_count,
-                  integrate_batch, measure_fp64_peak, rk4_f32_integrate_batch)
+                  integrate_batch, measure_fp64_peak, rk4_f32_integrate_batch, save)

@@ -182,6 +182,64 @@ class System:
         return System(self.sys_id, params)
 
 
+class DynSystem:
+    """A system whose state dimension is only known at run time: the `DVector` instantiation of the
+    crate (`System<f64, DVector<f64>>`, examples/kepler_orbit_dvector.rs:7,26,
+    examples/three_body_system_dvector.rs:5,22; src/rk4.rs:272-306). The kernels keep the state in
+    registers, so the dimension has to be a compile-time constant on the device: the first use with
+    a state of length n compiles (NVRTC) and caches the kernels specialised for DIM = n; the source
+    may use `DIM` (e.g. `for (int i = 0; i < DIM; ++i) ...`)."""
+
+    def __init__(self, name, n_params, rhs_body, solout_body=None, params=None):
+        self.name, self.n_params = name, int(n_params)
+        self.rhs_body, self.solout_body = rhs_body, solout_body
+        self.params = None if params is None else np.asarray(params, dtype=np.float64)
+        self._by_dim = {}
+
+    def resolve(self, dim):
+        dim = int(dim)
+        if dim < 1:
+            raise ValueError("empty state")
+        if dim not in self._by_dim:
+            self._by_dim[dim] = System.from_source("%s_dim%d" % (self.name, dim), dim, self.n_params, self.rhs_body,
+                                                   self.solout_body, self.params)
+        return self._by_dim[dim]
+
+    def with_params(self, params):
+        d = DynSystem(self.name, self.n_params, self.rhs_body, self.solout_body, params)
+        d._by_dim = {k: v.with_params(params) for k, v in self._by_dim.items()}
+        return d
+
+
+def _rust_display_f64(v):
+    """`format!("{}", v)` of an f64: shortest digits that round-trip, never an exponent, no ".0"."""
+    v = float(v)
+    if v != v:
+        return "NaN"
+    if v in (float("inf"), float("-inf")):
+        return "inf" if v > 0 else "-inf"
+    import decimal
+    s = format(decimal.Decimal(repr(v)), "f")
+    if "." in s:
+        s = s.rstrip("0").rstrip(".")
+    return s
+
+
+def save(times, states, filename):
+    """The `save()` of the crate's examples (examples/lorenz.rs:56-84 and the others): one line per
+    stored point, `x, y0, y1, ...` with Rust's `{}` formatting of f64, parent directory created."""
+    import os
+    d = os.path.dirname(filename)
+    if d:
+        os.makedirs(d, exist_ok=True)
+    with open(filename, "w") as f:
+        for t, st in zip(times, states):
+            f.write(_rust_display_f64(t))
+            for val in np.asarray(st, dtype=np.float64).reshape(-1):
+                f.write(", " + _rust_display_f64(val))
+            f.write("\n")
+
+
 # ------------------------------------------------------------------ configs
 def config_new(method, x, x_end, dx, rtol, atol, out_type=None):
     c = _abi.Config()
@@ -214,6 +272,11 @@ def integrate_batch(system, cfg, y0, params=None, out_cap=0, com_cap=0, ctx=None
     system.params). Returns an _abi.HostOutputs (numpy arrays; layouts in include/ode_b200.h).
     """
     lib = _abi.load()
+    if isinstance(system, DynSystem):  # runtime dimension: [dim, n] decides
+        y0 = np.asarray(y0, dtype=np.float64)
+        if y0.ndim != 2:
+            raise ValueError("a DynSystem needs y0 of shape [dim, n]")
+        system = system.resolve(y0.shape[0])
     y0 = np.ascontiguousarray(np.asarray(y0, dtype=np.float64).reshape(system.dim, -1))
     n = y0.shape[1]
     if params is None:
@@ -371,8 +434,10 @@ class _Stepper:
     method = None
 
     def __init__(self, f, cfg, y):
-        self.f, self.cfg = f, cfg
         self.y0 = np.asarray(y, dtype=np.float64).reshape(-1)
+        if isinstance(f, DynSystem):  # DVector state: its length is the dimension
+            f = f.resolve(self.y0.size)
+        self.f, self.cfg = f, cfg
         if self.y0.size != f.dim:
             raise ValueError("state has %d components, system %s needs %d" % (self.y0.size, f.name, f.dim))
         self._results = SolverResult()

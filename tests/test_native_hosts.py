@@ -47,3 +47,17 @@ def test_cpp_host_mirror_on_gpu(tmp_path):
                                     os.path.join(LIBDIR, "cpp"), os.path.join(ROOT, "tests", "cpp_host_smoke.cpp"),
                                     "-L", LIBDIR, "-lode_b200", "-o", exe], exe)
     assert "dopri5 test1" in out and "FAIL" not in out and out.count("ok") >= 3
+
+
+def test_save_formats_like_rust_display(tmp_path):
+    """ob.save mirrors the examples' save() (examples/lorenz.rs:56-84): `{}` of an f64 is the shortest
+    round-trip digits, positional, without a trailing `.0`"""
+    from ode_solvers_b200.api import _rust_display_f64 as f, save
+    assert f(1.0) == "1" and f(-0.0) == "-0" and f(0.1) == "0.1" and f(1.5) == "1.5"
+    assert f(1e-7) == "0.0000001" and f(1e21) == "1000000000000000000000" and f(123456789.125) == "123456789.125"
+    assert f(5e-324) == "0." + "0" * 323 + "5"
+    assert f(float("nan")) == "NaN" and f(float("inf")) == "inf" and f(float("-inf")) == "-inf"
+    assert f(-5007.248417988539) == "-5007.248417988539" and f(1.0 / 3.0) == "0.3333333333333333"
+    p = tmp_path / "outputs" / "x.dat"
+    save([0.0, 0.001], [[1.0, 1.0, 1.0], [1.0000000000000002, 2.5, -3e-5]], str(p))
+    assert p.read_text() == "0, 1, 1, 1\n0.001, 1.0000000000000002, 2.5, -0.00003\n"
