@@ -45,9 +45,10 @@ METRIC = "accepted trajectory-steps/sec (f64)"
 UNIT = "accepted_steps/s"
 # nominal algorithmic FP64 ops per ATTEMPTED Dopri5 step, 63n + 6F + 25 with n = 3, F = 8
 FLOPS_PER_ATTEMPT = 63 * 3 + 6 * 8 + 25
-# from the committed ncu capture of this kernel on this workload (profiles/r1_ncu_summaries.json, "r1d")
-NCU_DRAM_BYTES_PER_LAUNCH = 30393856 + 13903104
-NCU_FP64_PIPE_BUSY = 0.708  # sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active / 100
+# from the committed ncu capture of this kernel on this workload (profiles/r1_ncu_summaries.json,
+# "r1e_lorenz_dopri5_final")
+NCU_DRAM_BYTES_PER_LAUNCH = 32995072 + 34777600
+NCU_FP64_PIPE_BUSY = 0.702  # sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active / 100
 
 
 def workload_config(n_gpus):
@@ -340,7 +341,7 @@ def run_native(args):
         "bound": "fp64", "achieved": achieved, "peak": peak_tflops_fma, "unit": "TFLOP/s",
         "frac": achieved / peak_tflops_fma, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this "
-                          "kernel on this workload (profiles/r1_ncu_summaries.json, r1d): 30.4 MB + 13.9 MB",
+                          "kernel on this workload (profiles/r1_ncu_summaries.json, r1e_lorenz_dopri5_final): 33.0 MB + 34.8 MB",
         "fp64_pipe_busy_ncu": NCU_FP64_PIPE_BUSY,
         "kernel": "ode_step_loop_kernel<Dopri5Stepper<SysLorenz, Sparse>>",
         "peak_source": "measured live: DFMA-chain probe (ode_b200_measure_fp64_peak), FMA counted as 2 flops; "

@@ -1,0 +1,44 @@
+#!/usr/bin/env python3
+"""Collect selected metrics of `ncu --page raw --csv` exports into one JSON (profiles/*_ncu_summaries.json).
+usage: ncu_summary.py out.json label=raw.csv [label=raw.csv ...]"""
+import csv
+import json
+import sys
+
+KEEP = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+    "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed",
+    "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed",
+    "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed",
+    "sm__cycles_elapsed.avg", "sm__cycles_elapsed.avg.per_second", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "sm__icc_request_hit_rate.pct", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+]
+
+
+def main():
+    out = {}
+    for arg in sys.argv[2:]:
+        label, path = arg.split("=", 1)
+        rows = list(csv.reader(open(path)))
+        hdr, units, vals = rows[0], rows[1], rows[2]
+        d = {"kernel": vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else None}
+        for h, u, v in zip(hdr, units, vals):
+            if h in KEEP:
+                d[h] = {"value": v, "unit": u}
+        out[label] = d
+    json.dump(out, open(sys.argv[1], "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
