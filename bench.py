@@ -220,6 +220,12 @@ def run_native(args):
     dev = torch.device("cuda", local)
     lib = _abi.load()
     ctx = ob.Context(local)
+    # Up to 4 ranks per host the kernel stores its per-trajectory results straight into the pinned host
+    # arrays; with 8 ranks sharing the host's PCIe one DMA copy per array after the kernel is faster.
+    # Measured on this pool, ms per end-to-end pass at 1/2/4/8 ranks: zero-copy 29.2 / 29.2 / 30.0 /
+    # 37.5, staged copies 30.3 / 30.7 / 32.6 / 33.0 (profiles/r1_scaling_1_2_4_8.json).
+    zero_copy = world <= 4
+    ctx.set_zero_copy(zero_copy)
     n = N_PER_GPU
     f = ob.System.builtin("lorenz")
     cfg = ob.config_new(ob.DOPRI5, 0.0, X_END, 0.1, TOL, TOL, out_type=ob.OUT_SPARSE)
@@ -379,7 +385,9 @@ def run_native(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_s / args.steps, "kernel_ms_inside": e2e_kernel_ms,
                 "api": "ode_b200_integrate_batch (host pointers, pinned): y0/params by cudaMemcpyAsync, per-trajectory "
-                       "results written by the kernel straight into the pinned host arrays over PCIe"},
+                       "results " + ("written by the kernel straight into the pinned host arrays over PCIe" if zero_copy
+                                     else "copied back by cudaMemcpyAsync (ode_b200_set_zero_copy(ctx, 0): 8 "
+                                          "ranks share the host's PCIe)")},
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
         "roofline": roofline,

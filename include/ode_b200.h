@@ -255,6 +255,11 @@ int ode_b200_rk4_f32_integrate_batch(ode_b200_ctx* ctx, int sys_id, float x, flo
 /* kernel scheduling knob: 1 (default) = persistent kernel with lane refill from a work
  * queue; 0 = static one-thread-per-trajectory launch (kept for the ablation in DESIGN.md) */
 int ode_b200_set_work_queue(ode_b200_ctx* ctx, int enabled);
+/* host-buffer entry: 1 (default) = per-trajectory results are stored by the kernel straight into the
+ * caller's arrays when those are pinned, device-mapped host memory (no copy-back phase; best for one
+ * GPU per host); 0 = always through device buffers and one DMA copy per array (better when several
+ * GPUs share the host's PCIe) */
+int ode_b200_set_zero_copy(ode_b200_ctx* ctx, int enabled);
 
 /* ---- ContinuousOutputModel::evaluate, batched on the device ---------------------- */
 /*

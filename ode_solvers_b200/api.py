@@ -114,6 +114,11 @@ class Context:
     def set_work_queue(self, enabled):
         _check(self._lib.ode_b200_set_work_queue(self.handle, int(bool(enabled))), "set_work_queue")
 
+    def set_zero_copy(self, enabled):
+        """host-buffer entry: store per-trajectory results straight into pinned host arrays (default)
+        or go through device buffers and DMA copies (better when several GPUs share the host's PCIe)"""
+        _check(self._lib.ode_b200_set_zero_copy(self.handle, int(bool(enabled))), "set_zero_copy")
+
     @property
     def last_kernel_ms(self):
         return float(self._lib.ode_b200_last_kernel_ms(self.handle))

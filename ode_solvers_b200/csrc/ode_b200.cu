@@ -225,6 +225,7 @@ struct ode_b200_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     int use_queue = 1;
+    int zero_copy = 1; /* per-trajectory results straight into pinned host arrays (ode_b200_set_zero_copy) */
     unsigned long long* queue = nullptr;
     uint64_t launches = 0;
     double last_ms = 0.0;
@@ -295,6 +296,11 @@ extern "C" double ode_b200_last_kernel_ms(const ode_b200_ctx* c) {
 }
 extern "C" uint64_t ode_b200_launch_count(const ode_b200_ctx* c) { return c ? c->launches : 0; }
 extern "C" void* ode_b200_stream(const ode_b200_ctx* c) { return c ? (void*)c->stream : nullptr; }
+extern "C" int ode_b200_set_zero_copy(ode_b200_ctx* c, int enabled) {
+    if (!c) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    c->zero_copy = enabled ? 1 : 0;
+    return ODE_B200_SUCCESS;
+}
 extern "C" int ode_b200_set_work_queue(ode_b200_ctx* c, int enabled) {
     if (!c) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
     c->use_queue = enabled ? 1 : 0;
@@ -497,7 +503,9 @@ static int integrate_range(ode_b200_ctx* c, int sys_id, const ode_b200_config* c
      * STRAIGHT into the caller's arrays when those are pinned, device-mapped host memory: the
      * stores trickle over PCIe while the kernel runs and no device-to-host copy phase is left
      * (bench.py: 1.2 ms of a 30.3 ms end-to-end pass). Pageable memory, sharded ranges of the SoA
-     * state and the large per-step arrays take the staged copy. */
+     * state and the large per-step arrays take the staged copy. When several GPUs share the host's
+     * PCIe the fine-grained stores lose against one DMA burst per array (8 ranks: 37.5 ms per pass
+     * against 33 ms); ode_b200_set_zero_copy(ctx, 0) selects the staged copy. */
     unsigned zero_copy = 0;
     int zc_bit = 0;
 #define WANT(field, buf, bytes)                                   \
@@ -509,7 +517,7 @@ static int integrate_range(ode_b200_ctx* c, int sys_id, const ode_b200_config* c
     {                                                                                          \
         ++zc_bit;                                                                              \
         if (out->field) {                                                                      \
-            void* mp = mapped_host_ptr(out->field);                                            \
+            void* mp = c->zero_copy ? mapped_host_ptr(out->field) : nullptr;                   \
             if (mp) {                                                                          \
                 dv.field = (decltype(dv.field))((char*)mp + (size_t)lo * (elem_bytes));        \
                 zero_copy |= 1u << zc_bit;                                                     \
@@ -520,7 +528,7 @@ static int integrate_range(ode_b200_ctx* c, int sys_id, const ode_b200_config* c
         }                                                                                      \
     }
     if (out->y_final) {
-        void* mp = (lo == 0 && n == n_total) ? mapped_host_ptr(out->y_final) : nullptr;
+        void* mp = (c->zero_copy && lo == 0 && n == n_total) ? mapped_host_ptr(out->y_final) : nullptr;
         if (mp) {
             dv.y_final = (double*)mp;
             zero_copy |= 1u;

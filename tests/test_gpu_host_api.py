@@ -311,11 +311,26 @@ def test_pinned_host_outputs_take_the_zero_copy_path_with_identical_results():
     rc = _abi.load().ode_b200_integrate_batch(ctx.handle, f.sys_id, C.byref(cfg), n, y0.ctypes.data, pp.ctypes.data,
                                              0, C.byref(o))
     assert rc == 0
-    assert same_f64(pin["y_final"].numpy(), ref.y_final).all()
-    assert same_f64(pin["x_final"].numpy(), ref.x_final).all() and same_f64(pin["h_next"].numpy(), ref.h_next).all()
-    for k in ("num_eval", "accepted", "rejected", "n_step"):
-        assert np.array_equal(pin[k].numpy().view(np.uint32), getattr(ref, k))
-    assert np.array_equal(pin["status"].numpy(), ref.status)
+
+    def check():
+        assert same_f64(pin["y_final"].numpy(), ref.y_final).all()
+        assert same_f64(pin["x_final"].numpy(), ref.x_final).all()
+        assert same_f64(pin["h_next"].numpy(), ref.h_next).all()
+        for k in ("num_eval", "accepted", "rejected", "n_step"):
+            assert np.array_equal(pin[k].numpy().view(np.uint32), getattr(ref, k))
+        assert np.array_equal(pin["status"].numpy(), ref.status)
+
+    check()
+    # ode_b200_set_zero_copy(ctx, 0): the same pinned arrays filled by DMA copies instead
+    for t in pin.values():
+        t.fill_(-7)
+    ctx2 = ob.Context(0)
+    ctx2.set_zero_copy(False)
+    rc = _abi.load().ode_b200_integrate_batch(ctx2.handle, f.sys_id, C.byref(cfg), n, y0.ctypes.data,
+                                             pp.ctypes.data, 0, C.byref(o))
+    assert rc == 0
+    check()
+    ctx2.close()
 
 
 def test_dop853_continuous_output_model_extension():
