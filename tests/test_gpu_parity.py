@@ -121,6 +121,34 @@ def test_work_queue_refills_lockstep_ctas_many_times():
     assert (g.h_next[sel].view(np.uint64) == o.h_next.view(np.uint64)).all()
 
 
+@pytest.mark.parametrize("cap", [2001, 2002, 2003, 2004, 1000])
+def test_staged_results_through_tma_bulk_copies(cap):
+    """output-heavy calls record through the shared-memory rings and per-lane TMA bulk copies: row
+    capacities of every residue mod 4 (padded device rows, tail groups written by the lane itself) and a
+    capacity that overflows (every push still counted), every sample bitwise"""
+    n = 1500
+    y0, p = W.lorenz_ensemble(n, offset=17)
+    for cfg in (ob.config_rk4(0.0, 2.0, 1e-3),                                  # 2001 samples, one per step
+                ob.config_new(ob.DOPRI5, 0.0, 20.0, 0.01, 1e-6, 1e-6)):        # Dense, 2001 samples, 0-3 per step
+        g, o = run_both("lorenz", cfg, y0, p, out_cap=cap)
+        assert_same_outputs(g, o, "staged m%d cap %d" % (cfg.method, cap))
+        assert (g.out_count == 2001).all()
+        assert ((g.status == ob.OUTPUT_CAPACITY_EXCEEDED) == (cap < 2001)).all()
+
+
+@pytest.mark.parametrize("com_cap", [901, 902, 399])
+def test_staged_continuous_output_model_intervals(com_cap):
+    """Dopri5 Continuous: samples and add_interval records (pairs of intervals per bulk copy) with odd /
+    even / overflowing capacities, ragged interval counts per trajectory"""
+    n = 1200
+    y0, p = W.lorenz_ensemble(n, offset=23)
+    cfg = ob.config_new(ob.DOPRI5, 0.0, 20.0, 0.1, 1e-6, 1e-6, out_type=ob.OUT_CONTINUOUS)
+    g, o = run_both("lorenz", cfg, y0, p, out_cap=com_cap + 1, com_cap=com_cap)
+    assert_same_outputs(g, o, "staged com cap %d" % com_cap)
+    assert g.com_count.min() > 300 and len(set(g.com_count.tolist())) > 50
+    assert (g.status == ob.OUTPUT_CAPACITY_EXCEEDED).any()  # some trajectories need more than 900 intervals
+
+
 def test_empty_batch():
     f = ob.System.builtin("lorenz")
     cfg = ob.config_new(ob.DOPRI5, 0.0, 1.0, 0.1, 1e-6, 1e-6)
