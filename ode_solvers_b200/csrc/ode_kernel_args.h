@@ -12,23 +12,17 @@ namespace ode_b200 {
  * instruction cache (Dop853 with n >= 6, everything with n > 8) run ONE 8-warp CTA per SM with all
  * 255 registers per thread and CTA-lockstep passes (run_lanes_, ode_device.cuh). Measured on B200:
  * CR3BP/Dop853/Dense 50.7 ms (4 x 128 threads) -> 38.4 (1 x 256) -> 33.5 (lockstep);
- * 3-body-18/Dop853 22.5 -> 16.8 -> 12.5. -DODE_B200_LOCKSTEP=0/1 forces it for measurements. */
+ * 3-body-18/Dop853 22.5 -> 16.8 -> 12.5 (128 or 192 threads: 13.2 / 12.8); Kepler/Dopri5 (n = 6, 19 KB
+ * of code per pass) gains nothing from it (90.7 against 87.0 ms with 4 x 128 threads).
+ * -DODE_B200_LOCKSTEP=0 switches it off for measurements. */
 __host__ __device__ constexpr bool lockstep_for(int dim, int method) {
-#ifdef ODE_B200_LOCKSTEP_ALL6
-    return dim >= 6 && method != ODE_B200_RK4;
-#elif defined(ODE_B200_LOCKSTEP)
+#ifdef ODE_B200_LOCKSTEP
     return ODE_B200_LOCKSTEP != 0 && (dim > 8 || (dim >= 6 && method == ODE_B200_DOP853));
 #else
     return dim > 8 || (dim >= 6 && method == ODE_B200_DOP853);
 #endif
 }
-#ifndef ODE_B200_BIG_THREADS
-#define ODE_B200_BIG_THREADS 256
-#endif
-__host__ __device__ constexpr int block_threads_for(int dim, int method) {
-    return lockstep_for(dim, method) ? (dim > 8 ? ODE_B200_BIG_THREADS : 256) : 128;
-}
-constexpr int kMaxBlockThreads = 256;
+__host__ __device__ constexpr int block_threads_for(int dim, int method) { return lockstep_for(dim, method) ? 256 : 128; }
 
 /*
  * Output staging. The per-step results are trajectory-major (one trajectory's samples are
