@@ -192,6 +192,12 @@ def other_workloads(ob, W, ctx, peak_inst):
                "accepted_steps_per_s": acc / (best * 1e-3), "attempted_steps": att,
                "algorithmic_tflops": flops * att / (best * 1e-3) / 1e12,
                "unfused_frac": flops * att / (best * 1e-3) / peak_inst, "trajectories_not_ok": int((o.status != 0).sum())}
+        if row["trajectories_not_ok"]:
+            st, cnt = np.unique(o.status[o.status != 0], return_counts=True)
+            names = {1: "MaxNumStepReached", 2: "StepSizeUnderflow", 3: "StiffnessDetected", 4: "OutputCapacityExceeded",
+                     5: "UnsupportedDomain"}
+            row["not_ok_statuses"] = {names.get(int(a), str(int(a))): int(b) for a, b in zip(st, cnt)}
+            row["not_ok_note"] = "IntegrationError results of the reference for these inputs (same statuses in the oracle)"
         if cap:
             stored = int(np.minimum(o.out_count, cap).sum()) * (1 + y0.shape[0]) * 8
             row["sample_bytes"] = stored
