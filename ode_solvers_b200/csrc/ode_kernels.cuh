@@ -14,9 +14,10 @@
  *  - tableau coefficients are compile-time immediates; terms whose coefficient is a
  *    structural zero are skipped (x + k*0.0 == x for finite k). To keep the reference's
  *    behaviour when a stage derivative is inf/NaN (there inf*0.0 = NaN poisons the error
- *    estimate and the step is rejected), the stages whose value could otherwise vanish
- *    behind skipped zeros (Dopri5: k2, whose a72 = e2 = d2 = 0; Dop853: k2..k5, whose b and e
- *    weights are 0) are tested with an integer-pipe exponent check and a hit forces err = NaN,
+ *    estimate and the step is rejected), the values that could otherwise vanish behind skipped
+ *    zeros (Dopri5: k2, whose a72 = e2 = d2 = 0; Dop853: k2..k5, whose b and e weights are 0, and
+ *    the 8th-order solution, which sits in a slot of the error sum with a zero weight)
+ *    are tested with an integer-pipe exponent check and a hit forces err = NaN,
  *    i.e. the same reject + h/facc1 shrink. Every other stage enters the error estimate with
  *    a non-zero weight, so a non-finite value there makes err non-finite by itself;
  *  - identical sub-expressions the source evaluates twice ((e/sc)*(e/sc), k*h) are computed
@@ -624,6 +625,10 @@ struct Dop853Stepper {
                        k[10][i] * c_dp8_b[10]) +
                       k[11][i] * c_dp8_b[11];
             y8[i] = y[i] + bsum[i] * h;
+            /* the reference's err_est runs over its 12 slots, of which slots 3 and 4 hold bsum and y8 by
+             * now, times e4 = e5 = 0 (dop853.rs:334-347): a non-finite y8 (which every non-finite bsum
+             * implies) poisons the error estimate there, e.g. for an infinite state component */
+            bad |= nonfinite_(y8[i]);
         }
         /* error estimators and norm, dop853.rs:334-362. err_est runs over the 12 slots; slots
          * 1..4 (k11, k12, bsum, y8) meet e2..e5 = 0 and are skipped. */
