@@ -29,11 +29,10 @@ __host__ __device__ constexpr int block_threads_for(int dim, int method) { retur
  * contiguous, like the crate's Vec), so a warp whose 32 lanes each push one sample writes 32
  * different 128-byte lines with 8-byte pieces (measured: 0.45-0.64 TB/s of useful writes).
  * In the STAGE variant of every kernel a lane collects its samples in a shared-memory ring of two
- * groups of stage_group(dim) samples; the moment a group is complete the lane itself hands it to
- * the TMA engine as two bulk copies (cp.async.bulk.global.shared::cta: the group's x values and its
- * y vectors, each a contiguous, 16-byte aligned range of the trajectory's slice of out_x / out_y)
- * and goes on filling the other group -- no store instructions, no warp-level flush in the step
- * loop. tools/micro/bulk_store.cu: 3.5-4.0 TB/s for this pattern on B200 (32 B + 96 B copies),
+ * groups of stage_group(dim) samples; the moment a group is complete the lane itself hands its y
+ * vectors to the TMA engine as one bulk copy (cp.async.bulk.global.shared::cta: a contiguous,
+ * 16-byte aligned range of the trajectory's slice of out_y), writes its x values with two 16-byte
+ * stores, and goes on filling the other group -- no warp-level flush in the step loop. tools/micro/bulk_store.cu: 3.5-4.0 TB/s for this pattern on B200 (32 B + 96 B copies),
  * 4.3-4.6 TB/s with whole 8-sample runs, against 1.1-1.4 TB/s for per-lane vector stores.
  * It needs an even row pitch (alignment) and shared memory, so the launcher picks it only for
  * output-heavy calls (rule in ode_b200.cu). Lane buffer: x[R] then y[R][dim], R = 2 groups.
@@ -44,7 +43,7 @@ __host__ __device__ constexpr int stage_samples(int dim) { return 2 * stage_grou
 __host__ __device__ constexpr int stage_stride(int dim) { return stage_samples(dim) * (1 + dim) + 2; }
 /* ContinuousOutputModel intervals (breakpoint, step size, m coefficient vectors) are staged the same
  * way when they fit: a ring of two groups of 2 intervals per lane -- break[4], step[4], coef[4][m][dim]
- * -- each group leaving as three bulk copies. 0 = written directly (large dim * m). */
+ * -- each group leaving as one bulk copy (coefficients) and two 16-byte stores. 0 = written directly (large dim * m). */
 __host__ __device__ constexpr int com_stage_stride(int dim, int m, int threads) {
     return (stage_stride(dim) + 4 * (2 + m * dim)) * threads * 8 <= 110 * 1024 ? 4 * (2 + m * dim) : 0;
 }
