@@ -405,8 +405,7 @@ static int launch_device(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg
     bool stage = ka.out.out_x != nullptr;
     if (stage && cfg->method != ODE_B200_RK4 && cfg->out_type == ODE_B200_OUT_DENSE) {
         const double samples = cfg->dx > 0.0 ? fabs(cfg->x_end - cfg->x0) / cfg->dx : 0.0;
-        static const double min_samples = getenv("ODE_B200_STAGE_MIN_SAMPLES") ? atof(getenv("ODE_B200_STAGE_MIN_SAMPLES")) : 1000.0;
-        stage = samples >= min_samples;
+        stage = samples >= 1000.0; /* measured: 201 samples 10.6 ms unstaged vs 12.2 staged; 2001 samples 37.4 vs 18.3 */
     }
     if (stage && ((ka.out_pitch & 1) != 0 || ((uintptr_t)ka.out.out_x & 15u) != 0 || ((uintptr_t)ka.out.out_y & 15u) != 0))
         stage = false;
