@@ -385,7 +385,7 @@ static int launch_device(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg
     if (ka.out.out_cap == 0) ka.out.out_x = ka.out.out_y = nullptr;
     if (ka.out.com_cap == 0) ka.out.com_break = ka.out.com_step = ka.out.com_coef = nullptr;
 
-    const int block = block_threads_for(s.dim, cfg->method);
+    const int block = block_threads_for(s.dim, cfg->method, records_dense(cfg->method, cfg->out_type));
     const long long blocks_all = (n + block - 1) / block;
 
     /* `accepted % n_stiff` panics in the reference when n_stiff == 0 */

@@ -22,7 +22,21 @@ __host__ __device__ constexpr bool lockstep_for(int dim, int method) {
     return dim > 8 || (dim >= 6 && method == ODE_B200_DOP853);
 #endif
 }
-__host__ __device__ constexpr int block_threads_for(int dim, int method) { return lockstep_for(dim, method) ? 256 : 128; }
+/* `records_dense`: the stepper keeps dense-output coefficients live (Dense, Continuous, Continuous8).
+ * A lockstep CTA is 12 warps at 168 registers where the state allows it (n = 6 Sparse: Kepler/Dop853
+ * 39.4 ms with 8 warps / 255 registers, 37.6 with 12 / 168, 39.1 with 16 / 128, 44.2 with 10), and 8
+ * warps with all 255 registers otherwise (CR3BP Dense: 32.1 against 35.7 ms with 12 warps). */
+#ifndef ODE_B200_LOCK_THREADS
+#define ODE_B200_LOCK_THREADS 384
+#endif
+__host__ __device__ constexpr int block_threads_for(int dim, int method, bool records_dense) {
+    return !lockstep_for(dim, method) ? 128 : (dim <= 8 && !records_dense) ? ODE_B200_LOCK_THREADS : 256;
+}
+__host__ __device__ constexpr bool records_dense(int method, int out_type) {
+    return method == ODE_B200_DOPRI5 ? (out_type == ODE_B200_OUT_DENSE || out_type == ODE_B200_OUT_CONTINUOUS)
+           : method == ODE_B200_DOP853 ? (out_type == ODE_B200_OUT_DENSE || out_type == ODE_B200_OUT_CONTINUOUS8)
+                                       : false;
+}
 
 /*
  * Output staging. The per-step results are trajectory-major (one trajectory's samples are

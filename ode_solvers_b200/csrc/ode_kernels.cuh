@@ -89,7 +89,7 @@ struct Rk4Stepper {
     static constexpr int kMinBlocks = min_blocks_for<N, ODE_B200_RK4, false>();
     static constexpr bool kSpec = spec_math_for<Sys, ODE_B200_RK4>();
     static constexpr bool kLockstep = lockstep_for(N, ODE_B200_RK4);
-    static constexpr int kThreads = block_threads_for(N, ODE_B200_RK4);
+    static constexpr int kThreads = block_threads_for(N, ODE_B200_RK4, false);
     static constexpr int kRefillIdle = kLockstep ? ODE_B200_REFILL_IDLE : ODE_B200_REFILL_IDLE_FREE;
     struct State {
         double y[N];
@@ -209,9 +209,9 @@ struct Dopri5Stepper {
     static constexpr int kMinBlocks = min_blocks_for<N, ODE_B200_DOPRI5, DENSE || CONT>();
     static constexpr bool kSpec = spec_math_for<Sys, ODE_B200_DOPRI5>();
     /* shared-memory ring of ContinuousOutputModel intervals (0: written directly) */
-    static constexpr int kCS = (STAGE && CONT) ? com_stage_stride(N, 5, block_threads_for(N, ODE_B200_DOPRI5)) : 0;
+    static constexpr int kCS = (STAGE && CONT) ? com_stage_stride(N, 5, block_threads_for(N, ODE_B200_DOPRI5, true)) : 0;
     static constexpr bool kLockstep = lockstep_for(N, ODE_B200_DOPRI5);
-    static constexpr int kThreads = block_threads_for(N, ODE_B200_DOPRI5);
+    static constexpr int kThreads = block_threads_for(N, ODE_B200_DOPRI5, DENSE || CONT);
     static constexpr int kRefillIdle = kLockstep ? ODE_B200_REFILL_IDLE : ODE_B200_REFILL_IDLE_FREE;
 
     struct State {
@@ -504,9 +504,9 @@ struct Dop853Stepper {
     static constexpr bool TRACK_LAST = DENSE && Sys::HAS_SOLOUT;
     static constexpr int kMinBlocks = min_blocks_for<N, ODE_B200_DOP853, DENSE || CONT8>();
     static constexpr bool kSpec = spec_math_for<Sys, ODE_B200_DOP853>();
-    static constexpr int kCS = (STAGE && CONT8) ? com_stage_stride(N, 8, block_threads_for(N, ODE_B200_DOP853)) : 0;
+    static constexpr int kCS = (STAGE && CONT8) ? com_stage_stride(N, 8, block_threads_for(N, ODE_B200_DOP853, true)) : 0;
     static constexpr bool kLockstep = lockstep_for(N, ODE_B200_DOP853);
-    static constexpr int kThreads = block_threads_for(N, ODE_B200_DOP853);
+    static constexpr int kThreads = block_threads_for(N, ODE_B200_DOP853, DENSE || CONT8);
     static constexpr int kRefillIdle = kLockstep ? ODE_B200_REFILL_IDLE : ODE_B200_REFILL_IDLE_FREE;
 
     struct State {

@@ -66,7 +66,13 @@ def perturb_inputs(seed, system, y0, p):
     return y0, p
 
 
-@pytest.mark.parametrize("seed", range(600))
+import os
+
+# ODE_B200_FUZZ_SEEDS="lo:hi" widens the hunt (e.g. 600:6000 runs in about a minute on a B200)
+_LO, _HI = (int(v) for v in os.environ.get("ODE_B200_FUZZ_SEEDS", "0:600").split(":"))
+
+
+@pytest.mark.parametrize("seed", range(_LO, _HI))
 def test_random_configuration_matches_oracle_bitwise(seed):
     system, cfg, n, cap = random_case(seed)
     y0, p = ENSEMBLES[system](n, offset=9000 + 50 * seed)
