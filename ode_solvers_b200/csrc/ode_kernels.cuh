@@ -34,11 +34,12 @@ namespace ode_b200 {
 /*
  * Resident CTAs per SM the register allocator must leave room for (Stepper::kMinBlocks).
  * The step loop is bound by dependent FP64 latency (ncu: "wait" is the top stall), so for small
- * states warps per scheduler matter more than a few spilled scalars; for n = 6 the balance
- * moves towards registers. Measured on B200, 2^20 trajectories, kernel ms at 2/3/4/5/6 CTAs:
- *   Lorenz  Dopri5  46.4 / 36.2 / 32.4 / 31.4 / 31.8      Lorenz  Dop853  28.9 / 23.7 / 22.2 / 21.7 / 22.7
- *   Kepler  Dopri5 133.3 /113.4 /105.9 /109.7 /118.6      Kepler  Dop853  55.2 / 67.0 / 64.2 / 60.0 / 62.1
- *   CR3BP Dop853 Dense (2^18) 63.3 / 58.6 / 55.4 / 69.5 / 102.2      3-body-18 Dop853 (2^18) 18.9 / 18.0 / 18.1 / - / 26.1
+ * states warps per scheduler matter more than a few spilled scalars. Measured on B200, 2^20
+ * trajectories, kernel ms at 3/4/5/6 CTAs of 128 threads (current code):
+ *   Lorenz Dopri5 32.8 / 29.7 / 28.5 / 28.7      Lorenz Dop853 20.9 / 20.4 / 20.8 / 21.3
+ *   Robertson Dop853 8.8 / 8.7 / 9.1 / 9.4       Lorenz Dopri5 Dense (2^18) 10.6 / 10.6 / - / 12.3
+ *   Kepler Dopri5 (2/3/4 CTAs) 91.2 / 86.8 / 87.0
+ * The big steppers (lockstep_for) run one CTA per SM, see ode_kernel_args.h.
  * -DODE_B200_MIN_BLOCKS=k overrides the table for such sweeps.
  */
 /*
@@ -73,10 +74,8 @@ constexpr int min_blocks_for() {
 #ifdef ODE_B200_MIN_BLOCKS
     return ODE_B200_MIN_BLOCKS;
 #else
-    if (lockstep_for(N, METHOD)) return 1; /* one 8-warp CTA per SM, 255 registers */
-    if (N <= 4) return DENSE ? 4 : 5; /* Dense/Continuous keep rcont[][] live: 96 registers spill */
-    if (N > 8) return 3;
-    if (METHOD == ODE_B200_DOP853) return DENSE ? 4 : 2;
+    if (lockstep_for(N, METHOD)) return 1; /* one CTA per SM */
+    if (N <= 4) return (DENSE || METHOD == ODE_B200_DOP853) ? 4 : 5; /* rcont[][] / 12 stages live: 96 registers spill */
     return 4;
 #endif
 }
