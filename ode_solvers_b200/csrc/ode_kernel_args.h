@@ -25,7 +25,8 @@ __host__ __device__ constexpr bool lockstep_for(int dim, int method) {
 /* `records_dense`: the stepper keeps dense-output coefficients live (Dense, Continuous, Continuous8).
  * A lockstep CTA is 12 warps at 168 registers where the state allows it (n = 6 Sparse: Kepler/Dop853
  * 39.4 ms with 8 warps / 255 registers, 37.6 with 12 / 168, 39.1 with 16 / 128, 44.2 with 10), and 8
- * warps with all 255 registers otherwise (CR3BP Dense: 32.1 against 35.7 ms with 12 warps). */
+ * warps with all 255 registers otherwise (CR3BP Dense: 32.1 against 35.7 ms with 12 warps; CR3BP Sparse
+ * 2^18: 23.2 -> 20.5 with 12; 3-body-18: 12.3 with 8 warps, 21.0 with 12, 30.1 with 16). */
 #ifndef ODE_B200_LOCK_THREADS
 #define ODE_B200_LOCK_THREADS 384
 #endif

@@ -51,6 +51,10 @@ def build(name, n):
     if name == "cr3bp_dp8_dense":
         y0, p = W.cr3bp_ensemble(n)
         return "cr3bp", ob.config_new(ob.DOP853, 0.0, 20.0, 0.5, 1e-12, 1e-12), y0, p, 43, 1395
+    if name == "cr3bp_dp8":
+        y0, p = W.cr3bp_ensemble(n)
+        return ("cr3bp", ob.config_new(ob.DOP853, 0.0, 20.0, 0.5, 1e-12, 1e-12, out_type=ob.OUT_SPARSE), y0, p, 0,
+                1395)
     if name == "threebody18_dp8":
         y0, p = W.threebody18_ensemble(n)
         return ("threebody18", ob.config_new(ob.DOP853, 0.0, 5.0, 0.1, 1e-9, 1e-9, out_type=ob.OUT_SPARSE), y0, p, 0,
