@@ -103,6 +103,11 @@ extern "C" {
         sys_id: c_int, cfg: *const ode_b200_config, n_traj: i64, y0: *const c_double, params: *const c_double,
         params_per_traj: c_int, n_gpus: c_int, out: *const ode_b200_outputs,
     ) -> c_int;
+    /// 1 (default): persistent lanes refill from a work queue; 0: one thread per trajectory.
+    pub fn ode_b200_set_work_queue(ctx: *mut ode_b200_ctx, enabled: c_int) -> c_int;
+    /// 1 (default): per-trajectory results are stored straight into pinned host arrays; 0: device
+    /// buffers + one DMA copy per array (hosts whose GPUs share PCIe with 7 others).
+    pub fn ode_b200_set_zero_copy(ctx: *mut ode_b200_ctx, enabled: c_int) -> c_int;
     pub fn ode_b200_com_evaluate(
         ctx: *mut ode_b200_ctx, n_traj: i64, dim: c_int, m: c_int, com_cap: i64, com_lower: *const c_double,
         com_break: *const c_double, com_step: *const c_double, com_coef: *const c_double, com_count: *const u32,

@@ -170,6 +170,13 @@ impl Context {
         if p.is_null() { Err(IntegrationError::Backend(last_error())) } else { Ok(Self(p)) }
     }
 }
+impl Context {
+    /// Host-buffer entry: store per-trajectory results straight into pinned host arrays (default) or
+    /// copy them back by DMA (`ode_b200_set_zero_copy`).
+    pub fn set_zero_copy(&self, enabled: bool) {
+        unsafe { ffi::ode_b200_set_zero_copy(self.0, enabled as std::os::raw::c_int) };
+    }
+}
 impl Drop for Context {
     fn drop(&mut self) {
         unsafe { ffi::ode_b200_destroy(self.0) }
