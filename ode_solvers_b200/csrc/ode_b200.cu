@@ -730,6 +730,10 @@ extern "C" int ode_b200_integrate_batch_multi(int sys_id, const ode_b200_config*
             ctxs.push_back(c);
         }
     }
+    /* up to 4 GPUs store their per-trajectory results straight into pinned host arrays; with more of
+     * them sharing the host's PCIe one DMA copy per array is faster (measured with 8 ranks: 33.0 against
+     * 37.5 ms per pass; with 4: 32.6 against 30.0) */
+    for (int g = 0; g < n_gpus; ++g) ctxs[g]->zero_copy = n_gpus <= 4 ? 1 : 0;
     const int64_t per = (n + n_gpus - 1) / n_gpus;
     std::vector<int> rcs(n_gpus, 0);
     std::vector<std::string> errs(n_gpus);
