@@ -181,30 +181,37 @@ def other_workloads(ob, W, ctx, peak_inst):
     ]
     rows = []
     for label, sysname, gen, n, cfg, cap, flops in cases:
-        y0, p = gen(n)
-        f = ob.System.builtin(sysname)
-        best = None
-        for _ in range(2 if cap else 3):
-            o = ob.integrate_batch(f, cfg, y0, p, out_cap=cap, ctx=ctx)
-            best = o.kernel_ms if best is None else min(best, o.kernel_ms)
-        acc, att = int(o.accepted.sum()), int(o.n_step.sum())
-        row = {"workload": label, "trajectories": n, "kernel_ms": round(best, 3),
-               "accepted_steps_per_s": acc / (best * 1e-3), "attempted_steps": att,
-               "algorithmic_tflops": flops * att / (best * 1e-3) / 1e12,
-               "unfused_frac": flops * att / (best * 1e-3) / peak_inst, "trajectories_not_ok": int((o.status != 0).sum())}
-        if row["trajectories_not_ok"]:
-            st, cnt = np.unique(o.status[o.status != 0], return_counts=True)
-            names = {1: "MaxNumStepReached", 2: "StepSizeUnderflow", 3: "StiffnessDetected", 4: "OutputCapacityExceeded",
-                     5: "UnsupportedDomain"}
-            row["not_ok_statuses"] = {names.get(int(a), str(int(a))): int(b) for a, b in zip(st, cnt)}
-            row["not_ok_note"] = "IntegrationError results of the reference for these inputs (same statuses in the oracle)"
-        if cap:
-            stored = int(np.minimum(o.out_count, cap).sum()) * (1 + y0.shape[0]) * 8
-            row["sample_bytes"] = stored
-            row["sample_write_gbs"] = stored / (best * 1e-3) / 1e9
-        rows.append(row)
-        del o
+        try:
+            rows.append(_one_workload(ob, ctx, peak_inst, label, sysname, gen, n, cfg, cap, flops))
+        except Exception as e:
+            rows.append({"workload": label, "error": repr(e)})
     return rows
+
+
+def _one_workload(ob, ctx, peak_inst, label, sysname, gen, n, cfg, cap, flops):
+    y0, p = gen(n)
+    f = ob.System.builtin(sysname)
+    best = None
+    for _ in range(2 if cap else 3):
+        o = ob.integrate_batch(f, cfg, y0, p, out_cap=cap, ctx=ctx)
+        best = o.kernel_ms if best is None else min(best, o.kernel_ms)
+    acc, att = int(o.accepted.sum()), int(o.n_step.sum())
+    row = {"workload": label, "trajectories": n, "kernel_ms": round(best, 3),
+           "accepted_steps_per_s": acc / (best * 1e-3), "attempted_steps": att,
+           "algorithmic_tflops": flops * att / (best * 1e-3) / 1e12,
+           "unfused_frac": flops * att / (best * 1e-3) / peak_inst, "trajectories_not_ok": int((o.status != 0).sum())}
+    if row["trajectories_not_ok"]:
+        st, cnt = np.unique(o.status[o.status != 0], return_counts=True)
+        names = {1: "MaxNumStepReached", 2: "StepSizeUnderflow", 3: "StiffnessDetected", 4: "OutputCapacityExceeded",
+                 5: "UnsupportedDomain"}
+        row["not_ok_statuses"] = {names.get(int(a), str(int(a))): int(b) for a, b in zip(st, cnt)}
+        row["not_ok_note"] = "IntegrationError results of the reference for these inputs (same statuses in the oracle)"
+    if cap:
+        stored = int(np.minimum(o.out_count, cap).sum()) * (1 + y0.shape[0]) * 8
+        row["sample_bytes"] = stored
+        row["sample_write_gbs"] = stored / (best * 1e-3) / 1e9
+    del o
+    return row
 
 
 # ---------------------------------------------------------------- native arm (GPU)
@@ -382,7 +389,10 @@ def run_native(args):
     # ---- the other BASELINE.json configs on the same kernels (N = 1 only; reported, not the metric)
     others = None
     if world == 1 and not args.no_extra:
-        others = other_workloads(ob, workloads, ctx, peak_inst)
+        try:
+            others = other_workloads(ob, workloads, ctx, peak_inst)
+        except Exception as e:  # reported workloads must never cost the headline line
+            others = {"error": repr(e)}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
