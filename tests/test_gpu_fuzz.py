@@ -80,7 +80,13 @@ def test_random_configuration_matches_oracle_bitwise(seed):
     com = cap if cfg.out_type in (ob.OUT_CONTINUOUS, ob.OUT_CONTINUOUS8) else 0
     if cfg.method == ob.RK4 or (cfg.method == ob.DOP853 and cfg.out_type == ob.OUT_CONTINUOUS):
         com = 0  # Dop853 treats Continuous like Sparse (dop853.rs:398,540-542)
-    g, o = run_both(system, cfg, y0, p, out_cap=cap, com_cap=com)
+    ctx = None
+    if seed % 5 == 4:  # the static one-thread-per-trajectory schedule must give the same bits
+        ctx = ob.Context(0)
+        ctx.set_work_queue(False)
+    g, o = run_both(system, cfg, y0, p, out_cap=cap, com_cap=com, ctx=ctx)
+    if ctx is not None:
+        ctx.close()
     label = "fuzz %d: %s m%d o%d x %g->%g dx %g rtol %.2e atol %.2e beta %g n_max %d n_stiff %d cap %d" % (
         seed, system, cfg.method, cfg.out_type, cfg.x0, cfg.x_end, cfg.dx, cfg.rtol, cfg.atol, cfg.beta, cfg.n_max,
         cfg.n_stiff, cap)
