@@ -53,3 +53,32 @@ def test_f32_only_where_the_rhs_has_an_f32_form():
     with pytest.raises(ob.Ode200Error) as e:
         ob.rk4_f32_integrate_batch(ob.System.builtin("kepler"), 0.0, 1.0, 0.1, np.ones((6, 4)), [1.0])
     assert "no f32 instantiation" in str(e.value)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_f32_random_configurations_bitwise(seed):
+    """random systems, spans, step sizes (incl. negative and non-dividing ones), capacities and
+    non-finite states for the f32 fixed-step path"""
+    rng = np.random.default_rng(77 + seed)
+    system = str(rng.choice(["lorenz", "robertson", "bouncing_ball", "test_rk4_1", "test_rk4_2"]))
+    n = int(rng.choice([1, 33, 200]))
+    if system == "lorenz":
+        y0, p = W.lorenz_ensemble(n, offset=seed)
+        span = 1.0
+    elif system == "robertson":
+        y0, p = W.robertson_sweep(n, offset=seed)
+        span = 0.01
+    elif system == "bouncing_ball":
+        y0, p = W.bouncing_ball_ensemble(n, offset=seed)
+        span = 5.0
+    else:
+        y0, p = rng.uniform(-2, 2, (1, n)), None
+        span = 1.0
+    steps = int(rng.choice([3, 10, 250, 1000]))
+    step = span / steps * float(rng.choice([1.0, 1.0, 1.0001, 0.37])) * (1.0 if rng.random() < 0.9 else -1.0)
+    x0 = float(rng.choice([0.0, 0.25 * span]))
+    if rng.random() < 0.1:
+        y0 = y0.copy()
+        y0[0, ::5] = rng.choice([np.inf, np.nan, 3e38, -3e38, 1e-45])
+    cap = int(rng.choice([0, 4, steps + 2, 2 * steps + 5]))
+    check(system, x0, x0 + span, step, y0, p, cap)
