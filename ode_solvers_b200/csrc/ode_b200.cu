@@ -720,15 +720,15 @@ extern "C" int ode_b200_integrate_batch_multi(int sys_id, const ode_b200_config*
     const int avail = ode_b200_device_count();
     if (avail <= 0) return fail(ODE_B200_ERR_NO_DEVICE, "no CUDA device available (no CPU fallback)");
     if (n_gpus < 1 || n_gpus > avail) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "n_gpus out of range");
+    /* this entry owns one internal context per GPU: concurrent callers take turns (callers that want
+     * to overlap use their own contexts and ode_b200_integrate_batch per GPU) */
     static std::mutex mu;
     static std::vector<ode_b200_ctx*> ctxs;
-    {
-        std::lock_guard<std::mutex> g(mu);
-        while ((int)ctxs.size() < n_gpus) {
-            ode_b200_ctx* c = ode_b200_create((int)ctxs.size());
-            if (!c) return ODE_B200_ERR_CUDA;
-            ctxs.push_back(c);
-        }
+    std::lock_guard<std::mutex> whole_call(mu);
+    while ((int)ctxs.size() < n_gpus) {
+        ode_b200_ctx* c = ode_b200_create((int)ctxs.size());
+        if (!c) return ODE_B200_ERR_CUDA;
+        ctxs.push_back(c);
     }
     /* up to 4 GPUs store their per-trajectory results straight into pinned host arrays; with more of
      * them sharing the host's PCIe one DMA copy per array is faster (measured with 8 ranks: 33.0 against
