@@ -624,10 +624,6 @@ struct Dop853Stepper {
                        k[10][i] * c_dp8_b[10]) +
                       k[11][i] * c_dp8_b[11];
             y8[i] = y[i] + bsum[i] * h;
-            /* the reference's err_est runs over its 12 slots, of which slots 3 and 4 hold bsum and y8 by
-             * now, times e4 = e5 = 0 (dop853.rs:334-347): a non-finite y8 (which every non-finite bsum
-             * implies) poisons the error estimate there, e.g. for an infinite state component */
-            bad |= nonfinite_(y8[i]);
         }
         /* error estimators and norm, dop853.rs:334-362. err_est runs over the 12 slots; slots
          * 1..4 (k11, k12, bsum, y8) meet e2..e5 = 0 and are skipped. */
@@ -645,6 +641,10 @@ struct Dop853Stepper {
             const double eb = ((bsum[i] - k[0][i] * c_dp8_bhh[0]) - k[8][i] * c_dp8_bhh[1]) -
                               k[11][i] * c_dp8_bhh[2];
             const double sc = cfg.atol + fmax(fabs(y[i]), fabs(y8[i])) * cfg.rtol;
+            /* the reference's err_est runs over its 12 slots, of which slots 3 and 4 hold bsum and y8 by
+             * now, times e4 = e5 = 0 (dop853.rs:334-347): a non-finite y8 (which every non-finite bsum
+             * implies) poisons the error estimate there, e.g. for an infinite state component */
+            bad |= nonfinite_(y8[i]);
             /* err_est_i / sc_i and err_bhh_i / sc_i: one refined reciprocal, two exact quotients */
             const double rsc = m.rcp(sc);
             const double q1 = m.div_by(ee, sc, rsc), q2 = m.div_by(eb, sc, rsc);
