@@ -59,6 +59,10 @@ def build(name, n):
         y0, p = W.threebody18_ensemble(n)
         return ("threebody18", ob.config_new(ob.DOP853, 0.0, 5.0, 0.1, 1e-9, 1e-9, out_type=ob.OUT_SPARSE), y0, p, 0,
                 3708)
+    if name == "threebody18_dp8_com":   # config 3: Dop853 with dense output into a ContinuousOutputModel (extension)
+        y0, p = W.threebody18_ensemble(n)
+        return ("threebody18", ob.config_new(ob.DOP853, 0.0, 5.0, 0.1, 1e-9, 1e-9, out_type=ob.OUT_CONTINUOUS8), y0, p,
+                -120, 3708 + 153 * 18 + 3 * 90)
     if name == "robertson_dp8":
         y0, p = W.robertson_sweep(n)
         return ("robertson", ob.config_new(ob.DOP853, 0.0, 0.3, 0.3, 1e-2, 1e-6, out_type=ob.OUT_SPARSE), y0, p, 0,
@@ -91,7 +95,8 @@ def main():
                 dim = y0.shape[0]
                 stored = int(np.minimum(o.out_count, cap).sum()) * (1 + dim) * 8
                 if com_cap:
-                    stored += int(np.minimum(o.com_count, com_cap).sum()) * (5 * dim + 2) * 8
+                    m = 5 if cfg.method == ob.DOPRI5 else 8
+                    stored += int(np.minimum(o.com_count, com_cap).sum()) * (m * dim + 2) * 8
                 print("   output bytes written %.3f GB -> %.1f GB/s of HBM write (algorithmic)" % (
                     stored / 1e9, stored / 1e9 / (best * 1e-3)))
             acc, att = int(o.accepted.sum()), int(o.n_step.sum())
