@@ -755,67 +755,66 @@ struct Dop853Stepper {
                     rc[2][i] = bspl;
                     rc[3][i] = (ydiff - knew[i] * h) - bspl;
                 }
-                /* rcont[4..7] = sum_{j=1..12} slot[j-1]*d(i,j): columns 2..5 are zero; slot 10/11 = k11/k12 */
-                static_for<0, 4>([&](auto R) {
-                    constexpr int r = decltype(R)::value;
+                /* One pass per component, so that every stage value is read once (for n = 18 they live in
+                 * local memory) for all of:
+                 *  - rcont[4..7] = sum_{j=1..12} slot[j-1]*d(i,j): columns 2..5 are zero; slot 10/11 = k11/k12;
+                 *  - the arguments of the three extra stages 14, 15, 16 (dop853.rs:414-454): the left-
+                 *    associated sums of stages 15 and 16 end with the terms of k14 (and k15), which do not
+                 *    exist yet -- p15 / p16 are those sums up to the knew term, completed below in order. */
+                double yy[N], p15[N], p16[N], k14[N], k15[N], k16[N];
 #pragma unroll
-                    for (int i = 0; i < N; ++i) {
-                        double v = k[0][i] * c_dp8_d[r][0];
-                        v = v + k[5][i] * c_dp8_d[r][5];
-                        v = v + k[6][i] * c_dp8_d[r][6];
-                        v = v + k[7][i] * c_dp8_d[r][7];
-                        v = v + k[8][i] * c_dp8_d[r][8];
-                        v = v + k[9][i] * c_dp8_d[r][9];
-                        v = v + k[10][i] * c_dp8_d[r][10];
-                        v = v + k[11][i] * c_dp8_d[r][11];
+                for (int i = 0; i < N; ++i) {
+                    const double k0 = k[0][i], k5 = k[5][i], k6 = k[6][i], k7 = k[7][i], k8 = k[8][i], k9 = k[9][i],
+                                 k10 = k[10][i], k11 = k[11][i], kn = knew[i];
+                    static_for<0, 4>([&](auto R) {
+                        constexpr int r = decltype(R)::value;
+                        double v = k0 * c_dp8_d[r][0];
+                        v = v + k5 * c_dp8_d[r][5];
+                        v = v + k6 * c_dp8_d[r][6];
+                        v = v + k7 * c_dp8_d[r][7];
+                        v = v + k8 * c_dp8_d[r][8];
+                        v = v + k9 * c_dp8_d[r][9];
+                        v = v + k10 * c_dp8_d[r][10];
+                        v = v + k11 * c_dp8_d[r][11];
                         rc[4 + r][i] = v;
-                    }
-                });
-                /* the three extra stages 14, 15, 16 (dop853.rs:414-454) */
-                double yy[N], k14[N], k15[N], k16[N];
-#pragma unroll
-                for (int i = 0; i < N; ++i)
-                    yy[i] = s.y[i] + (((((((k[0][i] * c_dp8_a[13][0] + k[6][i] * c_dp8_a[13][6]) +
-                                            k[7][i] * c_dp8_a[13][7]) +
-                                           k[8][i] * c_dp8_a[13][8]) +
-                                          k[9][i] * c_dp8_a[13][9]) +
-                                         k[10][i] * c_dp8_a[13][10]) +
-                                        k[11][i] * c_dp8_a[13][11]) +
-                                       knew[i] * c_dp8_a[13][12]) *
+                    });
+                    yy[i] = s.y[i] + (((((((k0 * c_dp8_a[13][0] + k6 * c_dp8_a[13][6]) + k7 * c_dp8_a[13][7]) +
+                                           k8 * c_dp8_a[13][8]) +
+                                          k9 * c_dp8_a[13][9]) +
+                                         k10 * c_dp8_a[13][10]) +
+                                        k11 * c_dp8_a[13][11]) +
+                                       kn * c_dp8_a[13][12]) *
                                           h;
+                    p15[i] = (((((k0 * c_dp8_a[14][0] + k5 * c_dp8_a[14][5]) + k6 * c_dp8_a[14][6]) +
+                                k7 * c_dp8_a[14][7]) +
+                               k10 * c_dp8_a[14][10]) +
+                              k11 * c_dp8_a[14][11]) +
+                             kn * c_dp8_a[14][12];
+                    p16[i] = ((((k0 * c_dp8_a[15][0] + k5 * c_dp8_a[15][5]) + k6 * c_dp8_a[15][6]) +
+                               k7 * c_dp8_a[15][7]) +
+                              k8 * c_dp8_a[15][8]) +
+                             kn * c_dp8_a[15][12];
+                }
                 rhs_checked_<Sys>(x + h * c_dp8_c[13], yy, k14, s.p);
 #pragma unroll
-                for (int i = 0; i < N; ++i)
-                    yy[i] = s.y[i] + (((((((k[0][i] * c_dp8_a[14][0] + k[5][i] * c_dp8_a[14][5]) +
-                                            k[6][i] * c_dp8_a[14][6]) +
-                                           k[7][i] * c_dp8_a[14][7]) +
-                                          k[10][i] * c_dp8_a[14][10]) +
-                                         k[11][i] * c_dp8_a[14][11]) +
-                                        knew[i] * c_dp8_a[14][12]) +
-                                       k14[i] * c_dp8_a[14][13]) *
-                                          h;
+                for (int i = 0; i < N; ++i) yy[i] = s.y[i] + (p15[i] + k14[i] * c_dp8_a[14][13]) * h;
                 rhs_checked_<Sys>(x + h * c_dp8_c[14], yy, k15, s.p);
 #pragma unroll
                 for (int i = 0; i < N; ++i)
-                    yy[i] = s.y[i] + (((((((k[0][i] * c_dp8_a[15][0] + k[5][i] * c_dp8_a[15][5]) +
-                                            k[6][i] * c_dp8_a[15][6]) +
-                                           k[7][i] * c_dp8_a[15][7]) +
-                                          k[8][i] * c_dp8_a[15][8]) +
-                                         knew[i] * c_dp8_a[15][12]) +
-                                        k14[i] * c_dp8_a[15][13]) +
-                                       k15[i] * c_dp8_a[15][14]) *
-                                          h;
+                    yy[i] = s.y[i] + ((p16[i] + k14[i] * c_dp8_a[15][13]) + k15[i] * c_dp8_a[15][14]) * h;
                 rhs_checked_<Sys>(x + h * c_dp8_c[15], yy, k16, s.p);
                 s.c.num_eval += 3;
-                static_for<0, 4>([&](auto R) {
-                    constexpr int r = decltype(R)::value;
 #pragma unroll
-                    for (int i = 0; i < N; ++i)
-                        rc[4 + r][i] = ((((rc[4 + r][i] + knew[i] * c_dp8_d[r][12]) + k14[i] * c_dp8_d[r][13]) +
-                                         k15[i] * c_dp8_d[r][14]) +
-                                        k16[i] * c_dp8_d[r][15]) *
+                for (int i = 0; i < N; ++i) {
+                    const double kn = knew[i], ka = k14[i], kb = k15[i], kc = k16[i];
+                    static_for<0, 4>([&](auto R) {
+                        constexpr int r = decltype(R)::value;
+                        rc[4 + r][i] = ((((rc[4 + r][i] + kn * c_dp8_d[r][12]) + ka * c_dp8_d[r][13]) +
+                                         kb * c_dp8_d[r][14]) +
+                                        kc * c_dp8_d[r][15]) *
                                        h;
-                });
+                    });
+                }
             }
 #pragma unroll
             for (int i = 0; i < N; ++i) {
