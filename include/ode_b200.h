@@ -279,6 +279,8 @@ double ode_b200_tableau(const char* which, int i, int j);
 /* evaluate the device pow()/exp() clones on the GPU for n inputs (host pointers) */
 int ode_b200_debug_pow(ode_b200_ctx* ctx, int64_t n, const double* x, const double* y, double* out);
 int ode_b200_debug_exp(ode_b200_ctx* ctx, int64_t n, const double* x, double* out);
+/* the f32 powf clone (ode_powf.h: groundwork for the f32 adaptive steppers) evaluated on the GPU */
+int ode_b200_debug_powf(ode_b200_ctx* ctx, int64_t n, const float* x, const float* y, float* out);
 /* the kernels' exact division / square root building blocks (must equal the IEEE result bit for
  * bit). mode 0: a/b; 1: a/b and -a/b through one shared reciprocal; 2..6: the step loop's
  * speculative arithmetic (2: div, 3: div_nz, 4: sqrt(a), 5: sqrt_nz(a), 6: a/b and -a/b through one

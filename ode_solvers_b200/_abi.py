@@ -161,7 +161,7 @@ ABI_SYMBOLS = [
     "ode_b200_integrate_batch", "ode_b200_integrate_batch_device", "ode_b200_integrate_batch_multi",
     "ode_b200_rk4_f32_integrate_batch",
     "ode_b200_set_work_queue", "ode_b200_com_evaluate",
-    "ode_b200_tableau", "ode_b200_debug_pow", "ode_b200_debug_exp", "ode_b200_debug_div",
+    "ode_b200_tableau", "ode_b200_debug_pow", "ode_b200_debug_exp", "ode_b200_debug_div", "ode_b200_debug_powf",
 ]
 
 _lib = None

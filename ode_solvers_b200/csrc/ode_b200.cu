@@ -23,6 +23,7 @@
 
 #include "ode_b200.h"
 #include "ode_device.cuh"
+#include "ode_powf.h"
 #include "ode_jit.h"
 #include "ode_registry.h"
 
@@ -976,6 +977,37 @@ extern "C" int ode_b200_debug_div(ode_b200_ctx* c, int64_t n, const double* a, c
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(o, c->scratch2.p, n * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return ODE_B200_SUCCESS;
+}
+/* the f32 powf clone (ode_powf.h) on the device: tables in shared memory like the f64 ones */
+static __device__ const unsigned long long g_ode_powf_log2_tab[32] = ODE_POWF_LOG2_TAB_INIT;
+static __device__ const unsigned long long g_ode_exp2f_tab[32] = ODE_EXP2F_TAB_INIT;
+__global__ void debug_powf_kernel(long long n, const float* x, const float* y, float* o) {
+    __shared__ unsigned long long tabs[64];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) tabs[i] = i < 32 ? g_ode_powf_log2_tab[i] : g_ode_exp2f_tab[i - 32];
+    __syncthreads();
+    ode_powf_tabs T;
+    T.lt = tabs;
+    T.et = tabs + 32;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) o[i] = ode_powf(x[i], y[i], T);
+}
+extern "C" int ode_b200_debug_powf(ode_b200_ctx* c, int64_t n, const float* x, const float* y, float* o) {
+    if (!c) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    if (!x || !y || !o) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "NULL pointer");
+    if (n <= 0) return ODE_B200_SUCCESS;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (ensure(c, c->scratch0, n * 4) || ensure(c, c->scratch1, n * 4) || ensure(c, c->scratch2, n * 4))
+        return ODE_B200_ERR_CUDA;
+    cudaStream_t st = c->stream;
+    CUDA_TRY(cudaMemcpyAsync(c->scratch0.p, x, n * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(c->scratch1.p, y, n * 4, cudaMemcpyHostToDevice, st));
+    debug_powf_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, (const float*)c->scratch0.p,
+                                                                   (const float*)c->scratch1.p, (float*)c->scratch2.p);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(o, c->scratch2.p, n * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return ODE_B200_SUCCESS;
 }

@@ -8,6 +8,7 @@
 #include <stdint.h>
 #include <string.h>
 #include "../ode_solvers_b200/csrc/ode_pow.h"
+#include "../ode_solvers_b200/csrc/ode_powf.h"
 
 static int same_(double a, double b) {
     if (a != a && b != b) return 1;
@@ -37,6 +38,27 @@ int64_t ode_powcheck_exp(int64_t n, const double* x, double* out, double* ref) {
         if (out) out[i] = c;
         if (ref) ref[i] = l;
         bad += !same_(c, l);
+    }
+    return bad;
+}
+
+static int samef_(float a, float b) {
+    if (a != a && b != b) return 1;
+    uint32_t ua, ub;
+    memcpy(&ua, &a, 4);
+    memcpy(&ub, &b, 4);
+    return ua == ub;
+}
+
+/* the f32 clone (ode_powf.h) against libm's powf */
+int64_t ode_powcheck_powf(int64_t n, const float* x, const float* y, float* out, float* ref) {
+    ode_powf_tabs T = ode_powf_host_tabs();
+    int64_t bad = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        float c = ode_powf(x[i], y[i], T), l = powf(x[i], y[i]);
+        if (out) out[i] = c;
+        if (ref) ref[i] = l;
+        bad += !samef_(c, l);
     }
     return bad;
 }

@@ -1,5 +1,7 @@
 """Device pow()/exp() clones must be BIT-identical to the host libm the reference's
 f64::powf / f64::exp resolve to (controller.rs:53-54, dopri5.rs:236, dop853.rs:244)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -165,3 +167,36 @@ def test_speculative_div_and_sqrt_are_ieee_exact_or_flagged():
             out, fl = _spec(sp, sp, mode)
             assert same_f64(out[~fl], np.sqrt(sp)[~fl]).all()
             assert fl[~(sp >= 0)].all() and fl[np.isinf(sp)].all()
+
+
+def test_powf_clone_on_the_device_matches_libm():
+    """ode_powf.h (groundwork for the f32 adaptive steppers), device build, against the host's libm powf
+    (the host build of the same header is compared with libm in tests/test_pow_clone.py)"""
+    import ctypes as C
+    libm = C.CDLL("libm.so.6")
+    lib = _abi.load()
+    lib.ode_b200_debug_powf.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ode_b200_debug_powf.restype = C.c_int
+    chk = C.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "libode_powcheck.so"))
+    chk.ode_powcheck_powf.restype = C.c_int64
+    ctx = ob.default_context(0)
+    rng = np.random.default_rng(21)
+    n = 2_000_000
+    sp = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 1e-45, 1.1e-38, 3.4e38, 0.5, 2.0, 3.0, -3.0, 1e-30,
+                   1e30, 16777216.0, -2.5], dtype=np.float32)
+    SX, SY = np.meshgrid(sp, sp)
+    cases = [(10 ** rng.uniform(-12, 3, n), rng.choice([0.17, 0.125, -0.04, 0.2, 0.105], n)),
+             (np.ldexp(rng.uniform(1, 2, n), rng.integers(-149, 128, n)) * rng.choice([-1, 1], n), rng.uniform(-40, 40, n)),
+             (rng.uniform(-10, 10, n), rng.integers(-30, 30, n)), (np.full(n, 2.0), rng.uniform(-151, 129, n)),
+             (SX.ravel(), SY.ravel())]
+    for x, y in cases:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        y = np.ascontiguousarray(y, dtype=np.float32)
+        dev = np.zeros_like(x)
+        ref = np.zeros_like(x)
+        assert lib.ode_b200_debug_powf(ctx.handle, x.size, x.ctypes.data, y.ctypes.data, dev.ctypes.data) == 0
+        chk.ode_powcheck_powf(C.c_int64(x.size), C.c_void_p(x.ctypes.data), C.c_void_p(y.ctypes.data), None,
+                              C.c_void_p(ref.ctypes.data))  # ref = libm powf
+        same = (dev.view(np.uint32) == ref.view(np.uint32)) | (np.isnan(dev) & np.isnan(ref))
+        assert same.all(), (x[~same][:3], y[~same][:3], dev[~same][:3], ref[~same][:3])
+    del libm

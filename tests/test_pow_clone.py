@@ -68,3 +68,35 @@ def test_exp():
     sp = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-20, -1e-20, 709.78, 709.79, -745.1, -745.2, 1e-300])
     assert exp_mismatches(sp) == 0
     assert exp_mismatches(np.concatenate([10 ** rng.uniform(-30, 3, 100000), -10 ** rng.uniform(-30, 3, 100000)])) == 0
+
+
+# ---- f32: ode_powf.h (groundwork for the f32 instantiation of the adaptive steppers)
+def powf_mismatches(x, y):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.ascontiguousarray(np.broadcast_to(y, x.shape), dtype=np.float32)
+    f = _lib().ode_powcheck_powf
+    f.restype = C.c_int64
+    return f(C.c_int64(x.size), C.c_void_p(x.ctypes.data), C.c_void_p(y.ctypes.data), None, None)
+
+
+def test_powf_tables_match_running_libm():
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "extract_libm_powf_tables.py"), "--check"],
+                   check=True, stdout=subprocess.DEVNULL)
+
+
+def test_powf_matches_libm_bitwise():
+    """controller exponents (f32 alpha / -beta, hinit's 1/5 and 1/8), the whole float range, integer
+    exponents of negative bases, the overflow / underflow / may-underflow edges, every special case"""
+    rng = np.random.default_rng(14)
+    n = 1_000_000
+    for a in (0.2 - 0.04 * 0.75, 0.125, -0.04, 0.2, 0.125 - 0.1 * 0.2):
+        assert powf_mismatches(10 ** rng.uniform(-12, 3, n), a) == 0
+    wide = np.ldexp(rng.uniform(1, 2, n), rng.integers(-149, 128, n)).astype(np.float32) * rng.choice([-1, 1], n)
+    assert powf_mismatches(wide, rng.uniform(-40, 40, n)) == 0
+    assert powf_mismatches(rng.uniform(-10, 10, n), rng.integers(-30, 30, n).astype(np.float32)) == 0
+    assert powf_mismatches(np.exp(rng.uniform(-2, 2, n)), rng.uniform(-600, 600, n)) == 0
+    assert powf_mismatches(np.full(n, 2.0), rng.uniform(-151, 129, n)) == 0
+    sp = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 1e-45, 1.1e-38, 3.4e38, 0.5, 2.0, 3.0, -3.0, 1e-30,
+                   1e30, 16777216.0, 16777217.0, -2.5, 0.99999994, 1.0000001], dtype=np.float32)
+    X, Y = np.meshgrid(sp, sp)
+    assert powf_mismatches(X.ravel(), Y.ravel()) == 0
