@@ -193,7 +193,11 @@ int ode_b200_config_rk4(double x, double x_end, double step_size, ode_b200_confi
 /* ---- contexts ------------------------------------------------------------------- */
 ode_b200_ctx* ode_b200_create(int device);        /* NULL on failure (see last_error) */
 void          ode_b200_destroy(ode_b200_ctx*);
-/* device time of the most recent integrate kernel on this context, from CUDA events (ms) */
+/* Device time (ms, CUDA events) of the most recent step-loop kernel this context launched ON ITS OWN
+ * STREAM: every host-buffer entry, and ode_b200_integrate_batch_device when cuda_stream ==
+ * ode_b200_stream(ctx). A device-entry launch on a caller's stream is NOT timed (the caller owns that
+ * stream and times it itself); the value then still describes the last launch on the context stream
+ * (0.0 if there was none). Blocks until that kernel has finished. */
 double        ode_b200_last_kernel_ms(const ode_b200_ctx*);
 /* number of kernel launches issued by this context since creation */
 uint64_t      ode_b200_launch_count(const ode_b200_ctx*);
@@ -215,6 +219,9 @@ int ode_b200_integrate_batch(ode_b200_ctx* ctx, int sys_id, const ode_b200_confi
  * on the context's GPU and the kernel is enqueued on `cuda_stream` (a cudaStream_t passed as
  * void*; NULL = the CUDA default stream, as everywhere in CUDA) without synchronising.
  * ode_b200_stream(ctx) returns the context's own non-blocking stream.
+ * Launches of one context may be in flight on different streams at the same time (each launch owns
+ * one of 64 work-queue heads of the context, used round-robin): at most 64 un-finished launches per
+ * context. The context itself is not thread-safe: one host thread per context.
  */
 int ode_b200_integrate_batch_device(ode_b200_ctx* ctx, int sys_id, const ode_b200_config* cfg,
                                     int64_t n_traj, const double* y0, const double* params,

@@ -219,6 +219,10 @@ struct DevBuf {
     size_t cap = 0;
 };
 
+/* work-queue heads per context: launch k uses word k % kQueueSlots (more than kQueueSlots launches of
+ * one context in flight at once is not supported; include/ode_b200.h says so) */
+static constexpr unsigned kQueueSlots = 64;
+
 struct ode_b200_ctx {
     int device = 0;
     int num_sms = 0;
@@ -262,7 +266,7 @@ extern "C" ode_b200_ctx* ode_b200_create(int device) {
               cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess &&
               cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess &&
-              cudaMalloc((void**)&c->queue, 256) == cudaSuccess;
+              cudaMalloc((void**)&c->queue, kQueueSlots * sizeof(unsigned long long)) == cudaSuccess;
     if (!ok) {
         fail(ODE_B200_ERR_CUDA, std::string("context creation failed: ") + cudaGetErrorString(cudaGetLastError()));
         delete c;
@@ -379,7 +383,9 @@ static int launch_device(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg
     ka.params = params;
     ka.params_per_traj = per_traj ? 1 : 0;
     ka.use_queue = c->use_queue;
-    ka.queue = c->queue;
+    /* every launch gets its own work-queue head out of a ring of kQueueSlots words, so launches of one
+     * context that are in flight on different streams never share (or re-zero) a counter */
+    ka.queue = c->queue + (c->launches % kQueueSlots);
     ka.out = *out;
     ka.out_pitch = out_pitch > 0 ? out_pitch : out->out_cap;
     ka.com_pitch = com_pitch > 0 ? com_pitch : out->com_cap;
@@ -410,17 +416,19 @@ static int launch_device(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg
     }
     if (stage && ((ka.out_pitch & 1) != 0 || ((uintptr_t)ka.out.out_x & 15u) != 0 || ((uintptr_t)ka.out.out_y & 15u) != 0))
         stage = false;
-    /* coefficient vectors per interval of the continuous output model this call records (0: none) */
-    const int com_m = ka.out.com_break == nullptr ? 0
-                      : (cfg->method == ODE_B200_DOPRI5 && cfg->out_type == ODE_B200_OUT_CONTINUOUS)   ? 5
+    /* Coefficient vectors per interval of the continuous output model of this (method, out_type): the
+     * STAGE kernels of Dopri5/Continuous and Dop853/Continuous8 carry the interval ring in their
+     * compile-time shared-memory layout (Stepper::kCS) whether or not this call records the model,
+     * so the ring is sized from the same rule even when com_cap == 0 (com_break == NULL). */
+    const int com_m = (cfg->method == ODE_B200_DOPRI5 && cfg->out_type == ODE_B200_OUT_CONTINUOUS)   ? 5
                       : (cfg->method == ODE_B200_DOP853 && cfg->out_type == ODE_B200_OUT_CONTINUOUS8) ? 8
                                                                                                       : 0;
-    if (stage && com_m > 0 &&
+    if (stage && com_m > 0 && ka.out.com_break != nullptr &&
         ((ka.com_pitch & 1) != 0 || ((uintptr_t)ka.out.com_break & 15u) != 0 || ((uintptr_t)ka.out.com_step & 15u) != 0 ||
          ((uintptr_t)ka.out.com_coef & 15u) != 0))
         stage = false;
     const size_t dyn_smem = stage ? (size_t)stage_smem_doubles(s.dim, block, com_m) * sizeof(double) : 0;
-    CUDA_TRY(cudaMemsetAsync(c->queue, 0, sizeof(unsigned long long), stream));
+    CUDA_TRY(cudaMemsetAsync(ka.queue, 0, sizeof(unsigned long long), stream));
     if (stream == c->stream) CUDA_TRY(cudaEventRecord(c->ev0, stream));
     if (!s.jit) {
         const void* fn = kBuiltins[sys_id]->kernels[stage ? 1 : 0][cfg->method][cfg->out_type];
@@ -451,6 +459,7 @@ extern "C" int ode_b200_integrate_batch_device(ode_b200_ctx* c, int sys_id, cons
                                                int64_t n, const double* y0, const double* params, int per_traj,
                                                const ode_b200_outputs* out, void* cuda_stream) {
     if (!c) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    if (!cfg || !out) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "cfg / out is NULL");
     cudaStream_t st = (cudaStream_t)cuda_stream; /* NULL = the CUDA default stream */
     return launch_device(c, sys_id, cfg, n, y0, params, per_traj, out, out->out_cap, out->com_cap, st);
 }
@@ -472,9 +481,28 @@ static void* mapped_host_ptr(const void* host) {
  * caller's full-size arrays. [0, n_total) on one context is ode_b200_integrate_batch;
  * one range per GPU is the multi-GPU shard.
  */
+static int integrate_range_impl(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg, int64_t n_total, int64_t lo,
+                                int64_t hi, const double* y0, const double* params, int per_traj,
+                                const ode_b200_outputs* out);
+
+/* Never return while copies or zero-copy kernel stores that target the caller's arrays may still be
+ * in flight: an error in the middle of the enqueue sequence drains the stream first. */
 static int integrate_range(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg, int64_t n_total, int64_t lo,
                            int64_t hi, const double* y0, const double* params, int per_traj,
                            const ode_b200_outputs* out) {
+    const int rc = integrate_range_impl(c, sys_id, cfg, n_total, lo, hi, y0, params, per_traj, out);
+    if (rc != ODE_B200_SUCCESS && c && c->stream) {
+        const std::string keep = g_last_error;
+        cudaStreamSynchronize(c->stream);
+        cudaGetLastError();
+        g_last_error = keep;
+    }
+    return rc;
+}
+
+static int integrate_range_impl(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg, int64_t n_total, int64_t lo,
+                                int64_t hi, const double* y0, const double* params, int per_traj,
+                                const ode_b200_outputs* out) {
     SysInfo s;
     if (!sys_info(sys_id, &s)) return fail(ODE_B200_ERR_UNKNOWN_SYSTEM, "bad sys_id");
     if (int rc = validate(cfg, s, n_total, y0, params, out)) return rc;
@@ -633,10 +661,25 @@ extern "C" int ode_b200_integrate_batch(ode_b200_ctx* c, int sys_id, const ode_b
 }
 
 /* Rk4 with T = f32 (see include/ode_b200.h) */
+static int rk4_f32_impl(ode_b200_ctx* c, int sys_id, float x, float x_end, float step_size, int64_t n,
+                        const float* y0, const float* params, int per_traj, const ode_b200_outputs_f32* out);
+
 extern "C" int ode_b200_rk4_f32_integrate_batch(ode_b200_ctx* c, int sys_id, float x, float x_end, float step_size,
                                                 int64_t n, const float* y0, const float* params, int per_traj,
                                                 const ode_b200_outputs_f32* out) {
     if (!c) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    const int rc = rk4_f32_impl(c, sys_id, x, x_end, step_size, n, y0, params, per_traj, out);
+    if (rc != ODE_B200_SUCCESS && c->stream) { /* see integrate_range */
+        const std::string keep = g_last_error;
+        cudaStreamSynchronize(c->stream);
+        cudaGetLastError();
+        g_last_error = keep;
+    }
+    return rc;
+}
+
+static int rk4_f32_impl(ode_b200_ctx* c, int sys_id, float x, float x_end, float step_size, int64_t n,
+                        const float* y0, const float* params, int per_traj, const ode_b200_outputs_f32* out) {
     if (sys_id < 0 || sys_id >= kNumBuiltins) return fail(ODE_B200_ERR_UNKNOWN_SYSTEM, "f32 needs a built-in system");
     const SystemEntry* e = kBuiltins[sys_id];
     if (!e->rk4_f32_kernel)
@@ -665,7 +708,7 @@ extern "C" int ode_b200_rk4_f32_integrate_batch(ode_b200_ctx* c, int sys_id, flo
     ka.params = (const float*)c->params.p;
     ka.params_per_traj = per_traj ? 1 : 0;
     ka.use_queue = c->use_queue;
-    ka.queue = c->queue;
+    ka.queue = c->queue + (c->launches % kQueueSlots);
     ode_b200_outputs_f32& dv = ka.out;
 #define WANT32(field, buf, bytes)                                 \
     if (out->field) {                                             \
@@ -690,7 +733,7 @@ extern "C" int ode_b200_rk4_f32_integrate_batch(ode_b200_ctx* c, int sys_id, flo
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, e->rk4_f32_kernel, block, 0));
     long long grid = blocks_all;
     if (c->use_queue) grid = std::min<long long>(blocks_all, (long long)c->num_sms * std::max(per_sm, 1));
-    CUDA_TRY(cudaMemsetAsync(c->queue, 0, sizeof(unsigned long long), st));
+    CUDA_TRY(cudaMemsetAsync(ka.queue, 0, sizeof(unsigned long long), st));
     CUDA_TRY(cudaEventRecord(c->ev0, st));
     void* args[] = {&ka};
     CUDA_TRY(cudaLaunchKernel(e->rk4_f32_kernel, dim3((unsigned)grid), dim3(block), args, 0, st));
@@ -781,25 +824,29 @@ extern "C" int ode_b200_measure_fp64_peak(int device, double* inst_per_s, double
     int sms = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     double* sink = nullptr;
-    CUDA_TRY(cudaMalloc(&sink, 8));
-    cudaEvent_t e0, e1;
-    CUDA_TRY(cudaEventCreate(&e0));
-    CUDA_TRY(cudaEventCreate(&e1));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
     const int iters = 4096, grid = sms * 8, block = 256;
     double best = 0.0;
-    for (int rep = 0; rep < 5; ++rep) {
-        CUDA_TRY(cudaEventRecord(e0));
-        fp64_peak_kernel<<<grid, block>>>(sink, iters, 1.0 + rep);
-        CUDA_TRY(cudaEventRecord(e1));
-        CUDA_TRY(cudaEventSynchronize(e1));
+    cudaError_t err = cudaMalloc(&sink, 8);
+    if (err == cudaSuccess) err = cudaEventCreate(&e0);
+    if (err == cudaSuccess) err = cudaEventCreate(&e1);
+    for (int rep = 0; rep < 5 && err == cudaSuccess; ++rep) {
         float ms = 0.f;
-        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        err = cudaEventRecord(e0);
+        if (err == cudaSuccess) {
+            fp64_peak_kernel<<<grid, block>>>(sink, iters, 1.0 + rep);
+            err = cudaGetLastError();
+        }
+        if (err == cudaSuccess) err = cudaEventRecord(e1);
+        if (err == cudaSuccess) err = cudaEventSynchronize(e1);
+        if (err == cudaSuccess) err = cudaEventElapsedTime(&ms, e0, e1);
         const double inst = (double)grid * block * (double)iters * 16.0 * 8.0;
-        if (rep > 0) best = std::max(best, inst / (ms * 1e-3));
+        if (err == cudaSuccess && rep > 0) best = std::max(best, inst / (ms * 1e-3));
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(sink);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (sink) cudaFree(sink);
+    if (err != cudaSuccess) return fail(ODE_B200_ERR_CUDA, std::string("fp64 peak probe: ") + cudaGetErrorString(err));
     if (inst_per_s) *inst_per_s = best;
     /* 64 FP64 lanes per SM: implied SM clock if the pipe was saturated */
     if (sm_mhz_est) *sm_mhz_est = best / (64.0 * sms) * 1e-6;

@@ -15,11 +15,14 @@ namespace ode_b200 {
  * 3-body-18/Dop853 22.5 -> 16.8 -> 12.5 (128 or 192 threads: 13.2 / 12.8); Kepler/Dopri5 (n = 6, 19 KB
  * of code per pass) gains nothing from it (90.7 against 87.0 ms with 4 x 128 threads).
  * -DODE_B200_LOCKSTEP=0 switches it off for measurements. */
+#ifndef ODE_B200_LOCKSTEP_DP5
+#define ODE_B200_LOCKSTEP_DP5 0 /* 1: Dopri5 with n >= 6 runs lockstep CTAs too (measurement switch) */
+#endif
 __host__ __device__ constexpr bool lockstep_for(int dim, int method) {
 #ifdef ODE_B200_LOCKSTEP
     return ODE_B200_LOCKSTEP != 0 && (dim > 8 || (dim >= 6 && method == ODE_B200_DOP853));
 #else
-    return dim > 8 || (dim >= 6 && method == ODE_B200_DOP853);
+    return dim > 8 || (dim >= 6 && (method == ODE_B200_DOP853 || (ODE_B200_LOCKSTEP_DP5 && method == ODE_B200_DOPRI5)));
 #endif
 }
 /* `records_dense`: the stepper keeps dense-output coefficients live (Dense, Continuous, Continuous8).

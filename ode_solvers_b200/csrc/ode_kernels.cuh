@@ -22,6 +22,16 @@
  *    a non-zero weight, so a non-finite value there makes err non-finite by itself;
  *  - identical sub-expressions the source evaluates twice ((e/sc)*(e/sc), k*h) are computed
  *    once: same operands, same rounding, same bits.
+ *  - Signed zeros. A skipped term is +-0.0 for a finite stage value, and s + (+-0.0) == s bit for bit
+ *    unless s is -0.0 and the term +0.0 (the IEEE sum is then +0.0). The recorded dense coefficients
+ *    (Dop853 rcont[4..7]) are seeded with the source's +0.0 and are exact in the sign of zero too; the
+ *    error estimates only enter through their squares. What remains is a stage argument: a state
+ *    component that is exactly -0.0, whose every non-skipped term so far was -0.0 as well, meeting a
+ *    skipped term (Dopri5: a72; Dop853: the zero columns of a) that is +0.0 -- the reference then
+ *    hands +0.0 to the right-hand side where this kernel hands -0.0. No built-in system can tell the
+ *    two apart (no division by a state component, no atan2/copysign), and the sign is overwritten by
+ *    the next non-zero term; tests/test_gpu_edge_cases.py runs ensembles with -0.0 components, forward
+ *    and backward in x, bit for bit against the oracle (which adds every term).
  */
 #pragma once
 
@@ -768,7 +778,9 @@ struct Dop853Stepper {
                                  k10 = k[10][i], k11 = k[11][i], kn = knew[i];
                     static_for<0, 4>([&](auto R) {
                         constexpr int r = decltype(R)::value;
-                        double v = k0 * c_dp8_d[r][0];
+                        /* seeded with the source's zero vector (dop853.rs:411): (+0.0) + (-0.0) = +0.0, and
+                         * once the sum is not -0.0 the skipped (+-0.0) terms of columns 2..5 cannot change it */
+                        double v = 0.0 + k0 * c_dp8_d[r][0];
                         v = v + k5 * c_dp8_d[r][5];
                         v = v + k6 * c_dp8_d[r][6];
                         v = v + k7 * c_dp8_d[r][7];

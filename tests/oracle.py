@@ -12,7 +12,8 @@ from ode_solvers_b200 import _abi
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
-ORACLE_LIB = os.path.join(ORACLE_DIR, "libode_oracle.so")
+# ODE_ORACLE_LIB selects another build of the SAME oracle (the ASan/UBSan build of tests/test_sanitizers.py)
+ORACLE_LIB = os.environ.get("ODE_ORACLE_LIB") or os.path.join(ORACLE_DIR, "libode_oracle.so")
 
 _lib = None
 
@@ -25,7 +26,8 @@ def lib():
     global _lib
     if _lib is None:
         srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".c", ".h"))]
-        if (not os.path.exists(ORACLE_LIB)
+        if "ODE_ORACLE_LIB" not in os.environ and (
+                not os.path.exists(ORACLE_LIB)
                 or os.path.getmtime(ORACLE_LIB) < max(os.path.getmtime(s) for s in srcs)):
             build()
         l = C.CDLL(ORACLE_LIB)

@@ -98,3 +98,112 @@ def test_single_trajectory_and_huge_tolerance_edge():
         cfg = ob.config_new(ob.DOP853, 0.0, 1.0, 0.25, tol, tol)
         g, o = run_both("lorenz", cfg, y0, W.LORENZ_PARAMS, out_cap=8)
         assert_same_outputs(g, o, "tol %g" % tol)
+
+
+@pytest.mark.parametrize("system,method,out_type", [("lorenz", ob.DOPRI5, ob.OUT_CONTINUOUS),
+                                                    ("robertson", ob.DOPRI5, ob.OUT_CONTINUOUS),
+                                                    ("test_exp", ob.DOP853, ob.OUT_CONTINUOUS8),
+                                                    ("kepler", ob.DOPRI5, ob.OUT_CONTINUOUS)])
+def test_continuous_with_samples_but_without_model_capacity(system, method, out_type):
+    """OutputType::Continuous with out_cap > 0 and com_cap = 0: the staged kernels keep their interval ring
+    in the shared-memory layout whether or not the model is recorded (round-1 advisor finding: the launcher
+    sized the dynamic shared memory without it)."""
+    if system == "test_exp":
+        y0, p = np.linspace(0.5, 1.5, 300).reshape(1, -1), None
+        cfg = ob.config_new(method, 0.0, 1.0, 0.1, 1e-8, 1e-8, out_type=out_type)
+    elif system == "kepler":
+        y0, p = W.kepler_sweep(300)
+        cfg = ob.config_new(method, 0.0, W.kepler_period(), 60.0, 1e-8, 1e-8, out_type=out_type)
+    elif system == "robertson":
+        y0, p = W.robertson_sweep(300)
+        cfg = ob.config_new(method, 0.0, 0.3, 0.3, 1e-4, 1e-8, out_type=out_type)
+    else:
+        y0, p = W.lorenz_ensemble(300)
+        cfg = ob.config_new(method, 0.0, 2.0, 0.1, 1e-6, 1e-6, out_type=out_type)
+    g, o = run_both(system, cfg, y0, p, out_cap=400, com_cap=0)
+    assert_same_outputs(g, o, "%s continuous, com_cap=0" % system)
+    assert (g.com_count == g.accepted).all() and (g.out_count > 1).all()
+    g2, o2 = run_both(system, cfg, y0, p, out_cap=400, com_cap=400)  # and the recorded model still agrees
+    assert_same_outputs(g2, o2, "%s continuous, com_cap=400" % system)
+
+
+@pytest.mark.parametrize("method", [ob.RK4, ob.DOPRI5, ob.DOP853])
+def test_negative_zero_state_components(method):
+    """Signed zeros (round-1 advisor finding on the skipped zero-coefficient terms, see the header note of
+    ode_kernels.cuh): planar orbits with z = vz = -0.0 / +-0.0 mixtures, forward and backward, and a
+    Lorenz / bouncing-ball ensemble with -0.0 components, all bit for bit including the sign of zero."""
+    T = W.kepler_period()
+    y0, p = W.kepler_sweep(256)
+    signs = [(-0.0, -0.0), (-0.0, 0.0), (0.0, -0.0)]
+    for i in range(y0.shape[1]):
+        y0[2, i], y0[5, i] = signs[i % 3]
+    for x0, x1 in ((0.0, 1.5 * T), (1.5 * T, 0.0)):
+        cfg = ob.config_rk4(x0, x1, 30.0) if method == ob.RK4 else ob.config_new(
+            method, x0, x1, T / 16, 1e-9, 1e-9, out_type=ob.OUT_DENSE if x0 == 0.0 else ob.OUT_SPARSE)
+        g, o = run_both("kepler", cfg, y0, p, out_cap=900)
+        assert_same_outputs(g, o, "kepler -0.0 m%d %g->%g" % (method, x0, x1))
+    y0, p = W.lorenz_ensemble(192)
+    y0[0, ::2] = -0.0
+    y0[1, ::3] = -0.0
+    y0[2, ::5] = -0.0
+    y0[:, 7] = -0.0  # the fixed point at the origin, every component -0.0
+    cfg = ob.config_rk4(0.0, 1.0, 1e-2) if method == ob.RK4 else ob.config_new(method, 0.0, 2.0, 0.05, 1e-7, 1e-7)
+    out_type_runs = [cfg.out_type] if method == ob.RK4 else [ob.OUT_DENSE, ob.OUT_SPARSE] + (
+        [ob.OUT_CONTINUOUS] if method == ob.DOPRI5 else [ob.OUT_CONTINUOUS8])
+    for ot in out_type_runs:
+        cfg.out_type = ot
+        g, o = run_both("lorenz", cfg, y0, p, out_cap=400, com_cap=0 if method == ob.RK4 else 400)
+        assert_same_outputs(g, o, "lorenz -0.0 m%d o%d" % (method, ot))
+    y0, p = W.bouncing_ball_ensemble(128)
+    y0[2, :] = -0.0  # dy[2] = +0.0 (Q13): the state stays -0.0 + 0.0 * h
+    cfg = ob.config_rk4(0.0, 2.0, 0.01) if method == ob.RK4 else ob.config_new(method, 0.0, 10.0, 0.01, 1e-2, 1e-6,
+                                                                                 out_type=ob.OUT_SPARSE)
+    g, o = run_both("bouncing_ball", cfg, y0, p, out_cap=300)
+    assert_same_outputs(g, o, "ball -0.0 m%d" % method)
+
+
+def test_two_launches_of_one_context_in_flight_on_different_streams():
+    """ode_b200_integrate_batch_device on two caller streams without synchronising in between: every launch
+    owns its work-queue head (round-1 advisor finding: they used to share one counter)."""
+    import ctypes as C
+
+    import torch
+    from ode_solvers_b200 import _abi
+    lib = _abi.load()
+    ctx = ob.Context(0)
+    dev = torch.device("cuda", 0)
+    f = ob.System.builtin("lorenz")
+    n = 40000
+    cfgs = [ob.config_new(ob.DOPRI5, 0.0, 6.0, 0.1, 1e-6, 1e-6, out_type=ob.OUT_SPARSE),
+            ob.config_new(ob.DOP853, 0.0, 4.0, 0.1, 1e-7, 1e-7, out_type=ob.OUT_SPARSE)]
+    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    runs = []
+    for rep in range(3):  # several rounds, alternating streams, nothing synchronised in between
+        for k, (cfg, st) in enumerate(zip(cfgs, streams)):
+            y0, p = W.lorenz_ensemble(n, offset=1000 * rep + 17 * k)
+            d_y0, d_p = torch.from_numpy(y0).to(dev), torch.from_numpy(np.asarray(p)).to(dev)
+            bufs = {"y_final": torch.full((3, n), float("nan"), dtype=torch.float64, device=dev),
+                    "accepted": torch.full((n,), -1, dtype=torch.int32, device=dev),
+                    "status": torch.full((n,), -9, dtype=torch.int32, device=dev)}
+            torch.cuda.synchronize()
+            o = _abi.Outputs()
+            o.y_final = C.cast(bufs["y_final"].data_ptr(), _abi.c_double_p)
+            o.accepted = C.cast(bufs["accepted"].data_ptr(), _abi.c_u32_p)
+            o.status = C.cast(bufs["status"].data_ptr(), _abi.c_i32_p)
+            runs.append((cfg, y0, p, bufs, d_y0, d_p, o, st))
+    for cfg, y0, p, bufs, d_y0, d_p, o, st in runs:
+        rc = lib.ode_b200_integrate_batch_device(ctx.handle, f.sys_id, C.byref(cfg), n, d_y0.data_ptr(), d_p.data_ptr(),
+                                                 0, C.byref(o), st.cuda_stream)
+        assert rc == 0, _abi.last_error()
+    torch.cuda.synchronize()
+    import oracle
+    for cfg, y0, p, bufs, *_ in runs:
+        ref = oracle.integrate_batch("lorenz", cfg, y0, p)
+        assert (bufs["status"].cpu().numpy() == 0).all(), "a trajectory was never integrated"
+        assert np.array_equal(bufs["accepted"].cpu().numpy().astype(np.uint32), ref.accepted)
+        assert np.array_equal(bufs["y_final"].cpu().numpy().view(np.uint64), ref.y_final.view(np.uint64))
+    # NULL outputs / config are rejected instead of dereferenced
+    assert lib.ode_b200_integrate_batch_device(ctx.handle, f.sys_id, C.byref(cfgs[0]), n, runs[0][4].data_ptr(),
+                                               runs[0][5].data_ptr(), 0, None, None) == -1
+    assert lib.ode_b200_integrate_batch_device(ctx.handle, f.sys_id, None, n, runs[0][4].data_ptr(),
+                                               runs[0][5].data_ptr(), 0, C.byref(runs[0][6]), None) == -1

@@ -27,8 +27,22 @@ def test_c_header_links_and_struct_layout(tmp_path):
                                     os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-L", LIBDIR, "-lode_b200",
                                     "-o", exe], exe)
     f = out.split()
-    assert f[1] == "1"
+    assert int(f[1]) == _abi.load().ode_b200_abi_version()
     assert int(f[3]) == C.sizeof(_abi.Config) and int(f[5]) == C.sizeof(_abi.Outputs)
+    # every field: offset and size of the C struct == the ctypes mirror (tests/oracle.py shares these mirrors
+    # with the product wrapper, so a layout bug would otherwise cancel on both sides of a parity test)
+    mirrors = {"ode_b200_config": _abi.Config, "ode_b200_outputs": _abi.Outputs, "ode_b200_outputs_f32": _abi.OutputsF32}
+    seen = {k: [] for k in mirrors}
+    for line in out.splitlines():
+        if line.startswith("offset "):
+            _, name, off, size = line.split()
+            st, field = name.split(".")
+            d = getattr(mirrors[st], field)
+            assert (d.offset, d.size) == (int(off), int(size)), (name, d.offset, d.size, off, size)
+            seen[st].append(field)
+    for st, cls in mirrors.items():
+        assert seen[st] == [n for n, _ in cls._fields_], (st, seen[st])
+    assert "sizeof_outputs_f32 %d" % C.sizeof(_abi.OutputsF32) in out
     assert "alpha %.17g" % (0.2 - 0.04 * 0.75) in out and "n_max 100000" in out
 
 

@@ -1,0 +1,17 @@
+#!/bin/bash
+# One `ncu --set full` capture of the step-loop kernel of a tools/kbench.py workload (run on the GPU box
+# under gpurun, one GPU, only after the same command has exited 0 without ncu), exported as raw CSV into
+# gpurun_out/ and merged into a summaries JSON.
+# usage: tools/ncu_capture.sh <label> <kbench workload> <n trajectories> [summaries.json]
+set -e
+ROOT=$(cd "$(dirname "$0")/.." && pwd)
+LABEL=$1; WL=$2; N=$3; OUT=${4:-$ROOT/gpurun_out/r2_ncu_summaries.json}
+mkdir -p $ROOT/gpurun_out
+cd $ROOT
+KBENCH_N=$N KBENCH_REPS=1 python tools/kbench.py $WL > gpurun_out/plain_$LABEL.log 2>&1
+# -k regex: the step loop only; -s 0 -c 1: the first launch (kbench runs one with KBENCH_REPS=1)
+KBENCH_N=$N KBENCH_REPS=1 ncu --set full --clock-control none --import-source on -k regex:ode_step_loop -c 1 \
+    -f -o gpurun_out/$LABEL python tools/kbench.py $WL > gpurun_out/ncu_$LABEL.log 2>&1
+ncu -i gpurun_out/$LABEL.ncu-rep --page raw --csv > gpurun_out/${LABEL}_raw.csv
+python tools/ncu_summary.py $OUT $LABEL=gpurun_out/${LABEL}_raw.csv
+echo "captured $LABEL -> $OUT"

@@ -1,8 +1,10 @@
 #!/usr/bin/env python3
 """Collect selected metrics of `ncu --page raw --csv` exports into one JSON (profiles/*_ncu_summaries.json).
+An existing out.json is updated (labels given again are replaced), so captures can be added one at a time.
 usage: ncu_summary.py out.json label=raw.csv [label=raw.csv ...]"""
 import csv
 import json
+import os
 import sys
 
 KEEP = [
@@ -23,11 +25,16 @@ KEEP = [
     "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "lts__t_bytes.sum", "l1tex__t_bytes.sum", "smsp__inst_executed_op_shared_ld.sum", "smsp__inst_executed_op_shared_st.sum",
+    "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum",
+    "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__waves_per_multiprocessor",
 ]
 
 
 def main():
-    out = {}
+    out = json.load(open(sys.argv[1])) if os.path.exists(sys.argv[1]) else {}
     for arg in sys.argv[2:]:
         label, path = arg.split("=", 1)
         rows = list(csv.reader(open(path)))
