@@ -262,6 +262,10 @@ int ode_b200_rk4_f32_integrate_batch(ode_b200_ctx* ctx, int sys_id, float x, flo
 /* kernel scheduling knob: 1 (default) = persistent kernel with lane refill from a work
  * queue; 0 = static one-thread-per-trajectory launch (kept for the ablation in DESIGN.md) */
 int ode_b200_set_work_queue(ode_b200_ctx* ctx, int enabled);
+/* large states: 1 (default) = Dop853 runs one trajectory per group of three lanes for the systems that
+ * have that form (threebody18), the state and stage vectors dealt out component-wise so that they stay in
+ * registers; 0 = one trajectory per thread like everything else (kept for the ablation; same bits) */
+int ode_b200_set_lane_split(ode_b200_ctx* ctx, int enabled);
 /* host-buffer entry: 1 (default) = per-trajectory results are stored by the kernel straight into the
  * caller's arrays when those are pinned, device-mapped host memory (no copy-back phase; best for one
  * GPU per host); 0 = always through device buffers and one DMA copy per array (better when several

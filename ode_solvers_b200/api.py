@@ -119,6 +119,10 @@ class Context:
         or go through device buffers and DMA copies (better when several GPUs share the host's PCIe)"""
         _check(self._lib.ode_b200_set_zero_copy(self.handle, int(bool(enabled))), "set_zero_copy")
 
+    def set_lane_split(self, enabled):
+        """large states (threebody18 / Dop853): one trajectory per group of three lanes (default) or per thread"""
+        _check(self._lib.ode_b200_set_lane_split(self.handle, int(bool(enabled))), "set_lane_split")
+
     @property
     def last_kernel_ms(self):
         return float(self._lib.ode_b200_last_kernel_ms(self.handle))

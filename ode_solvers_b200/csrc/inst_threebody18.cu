@@ -1,2 +1,3 @@
 #include "ode_instantiate.cuh"
-ODE_B200_DEFINE_SYSTEM(SysThreeBody18, threebody18)
+#include "ode_split.cuh"
+ODE_B200_DEFINE_SYSTEM_WITH_SPLIT(SysThreeBody18, threebody18, SplitThreeBody18)

@@ -231,6 +231,7 @@ struct ode_b200_ctx {
     bool timed = false;
     int use_queue = 1;
     int zero_copy = 1; /* per-trajectory results straight into pinned host arrays (ode_b200_set_zero_copy) */
+    int lane_split = 1; /* large states: one trajectory per group of three lanes where the system has that form */
     unsigned long long* queue = nullptr;
     uint64_t launches = 0;
     double last_ms = 0.0;
@@ -304,6 +305,11 @@ extern "C" void* ode_b200_stream(const ode_b200_ctx* c) { return c ? (void*)c->s
 extern "C" int ode_b200_set_zero_copy(ode_b200_ctx* c, int enabled) {
     if (!c) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
     c->zero_copy = enabled ? 1 : 0;
+    return ODE_B200_SUCCESS;
+}
+extern "C" int ode_b200_set_lane_split(ode_b200_ctx* c, int enabled) {
+    if (!c) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    c->lane_split = enabled ? 1 : 0;
     return ODE_B200_SUCCESS;
 }
 extern "C" int ode_b200_set_work_queue(ode_b200_ctx* c, int enabled) {
@@ -392,8 +398,13 @@ static int launch_device(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg
     if (ka.out.out_cap == 0) ka.out.out_x = ka.out.out_y = nullptr;
     if (ka.out.com_cap == 0) ka.out.com_break = ka.out.com_step = ka.out.com_coef = nullptr;
 
-    const int block = block_threads_for(s.dim, cfg->method, records_dense(cfg->method, cfg->out_type));
-    const long long blocks_all = (n + block - 1) / block;
+    /* large states (ode_split.cuh): Dop853 with one trajectory per group of three lanes */
+    const void* split_fn = nullptr;
+    if (!s.jit && cfg->method == ODE_B200_DOP853 && c->lane_split) split_fn = kBuiltins[sys_id]->dop853_split_kernels[cfg->out_type];
+    const int block = split_fn ? kBuiltins[sys_id]->split_threads[cfg->out_type]
+                               : block_threads_for(s.dim, cfg->method, records_dense(cfg->method, cfg->out_type));
+    const long long traj_per_block = split_fn ? (long long)(block / 32) * kBuiltins[sys_id]->split_traj_per_warp : block;
+    const long long blocks_all = (n + traj_per_block - 1) / traj_per_block;
 
     /* `accepted % n_stiff` panics in the reference when n_stiff == 0 */
     if (cfg->method != ODE_B200_RK4 && cfg->n_stiff == 0) {
@@ -409,7 +420,7 @@ static int launch_device(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg
      * per trajectory the shared memory costs more occupancy than the stores cost time. The bulk copies
      * need 16-byte aligned rows: an even row pitch and aligned base pointers (always true for the
      * host-buffer entry, which pads its device rows). */
-    bool stage = ka.out.out_x != nullptr;
+    bool stage = ka.out.out_x != nullptr && split_fn == nullptr;
     if (stage && cfg->method != ODE_B200_RK4 && cfg->out_type == ODE_B200_OUT_DENSE) {
         const double samples = cfg->dx > 0.0 ? fabs(cfg->x_end - cfg->x0) / cfg->dx : 0.0;
         stage = samples >= 1000.0; /* measured: 201 samples 10.6 ms unstaged vs 12.2 staged; 2001 samples 37.4 vs 18.3 */
@@ -431,7 +442,7 @@ static int launch_device(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg
     CUDA_TRY(cudaMemsetAsync(ka.queue, 0, sizeof(unsigned long long), stream));
     if (stream == c->stream) CUDA_TRY(cudaEventRecord(c->ev0, stream));
     if (!s.jit) {
-        const void* fn = kBuiltins[sys_id]->kernels[stage ? 1 : 0][cfg->method][cfg->out_type];
+        const void* fn = split_fn ? split_fn : kBuiltins[sys_id]->kernels[stage ? 1 : 0][cfg->method][cfg->out_type];
         if (dyn_smem > 32 * 1024) /* static tables + dynamic rings may exceed the 48 KB default together */
             CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
         int per_sm = 0;

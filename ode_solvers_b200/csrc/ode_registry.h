@@ -15,6 +15,11 @@ struct SystemEntry {
     const void* kernels[2][3][4];
     /* Rk4 with T = f32 (nullptr when the system's RHS is f64-only) */
     const void* rk4_f32_kernel;
+    /* Dop853 with one trajectory per group of three lanes (ode_split.cuh), by out_type; nullptr: the
+     * system has no split form and runs one trajectory per thread */
+    const void* dop853_split_kernels[4];
+    int split_threads[4];         /* CTA size of each of them */
+    int split_traj_per_warp;      /* 10: lanes 30 and 31 stay idle */
 };
 
 }  // namespace ode_b200

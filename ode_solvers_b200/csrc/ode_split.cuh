@@ -1,0 +1,790 @@
+/*
+ * ode_split.cuh -- Dop853 for LARGE states (n = 18): one trajectory per GROUP OF THREE LANES.
+ *
+ * One trajectory per thread keeps k[12][n] in registers; for n = 18 that is 432 registers of stage
+ * values alone, and the round-1 kernel streamed them through local memory (ncu: 20 GB of DRAM writes
+ * per launch for 85 MB of results, FP64 pipe 30 % busy). Every component of every stage sum, of the
+ * 8th-order solution, of the error estimators and of the dense-output coefficients depends on that
+ * component only (dop853.rs:307-347, 398-480), so the components of a trajectory are dealt out to three
+ * adjacent lanes (six components each: exactly the register footprint of the n = 6 kernels, no local
+ * memory) and the lanes meet only where the reference couples components:
+ *   - the right-hand side: a split system (SplitThreeBody18 below) evaluates its own part of f and
+ *     exchanges what the others need with warp shuffles;
+ *   - the three norms of hinit, the two error norms and the stiffness quotients, which the reference
+ *     accumulates over the components IN INDEX ORDER (dop853.rs:349-356): the running sum is handed
+ *     from lane to lane in that order, so every lane of the group ends up with the reference's bits
+ *     and takes the same accept / reject decision on its own.
+ * Lanes 30 and 31 of a warp stay idle (10 trajectories per warp).
+ *
+ * Shuffles need every named lane, so all code that contains one is executed by the WHOLE warp
+ * (full-mask shuffles compile to a bare SHFL; a per-group mask costs a MATCH + VOTE + branch each and
+ * splits the straight-line block): a pass is split into per-lane phases without shuffles (the
+ * controller's commit, result stores, the dense sampling loop) and warp-uniform phases (the attempt
+ * itself, the prologue of newly claimed trajectories, the three extra dense stages) in which lanes
+ * without work compute on stale values and commit nothing.
+ *
+ * Bit parity: per component the operations and their order are those of Dop853Stepper
+ * (ode_kernels.cuh), which the parity tests hold bit for bit against the oracle; the only new
+ * arithmetic is the order of the cross-component sums, reproduced exactly as described above.
+ */
+#pragma once
+
+#include "ode_kernels.cuh"
+#include "ode_systems.cuh"
+
+namespace ode_b200 {
+
+constexpr unsigned kFullMask = 0xffffffffu;
+
+/* a lane's place in its group of three */
+struct Lane3 {
+    unsigned role, base, next, prev;
+    bool valid;
+    ODE_DEV void init() {
+        const unsigned lane = threadIdx.x & 31u;
+        role = lane % 3u;
+        base = lane - role;
+        valid = lane < 30u;
+        next = base + (role + 1u) % 3u; /* lanes 30/31 name lanes that do not exist: SHFL wraps, nobody reads it */
+        prev = base + (role + 2u) % 3u;
+    }
+};
+
+ODE_DEV double shfl_d_(double v, unsigned src) { return __shfl_sync(kFullMask, v, (int)src); }
+ODE_DEV double neg_if_(double v, bool c) { /* exact: a sign flip */
+    return __hiloint2double(__double2hiint(v) ^ (c ? (int)0x80000000 : 0), __double2loint(v));
+}
+/* true for every lane of a group in which any lane holds true */
+ODE_DEV bool group_any_(const Lane3& L, bool b) { return ((__ballot_sync(kFullMask, b) >> L.base) & 7u) != 0u; }
+
+/* sum of squares in nalgebra's `dot` order (see diff_dot_, ode_device.cuh) of an already formed difference */
+template <int N>
+ODE_DEV double sq_dot_(const double (&d)[N]) {
+    static_assert(N > 4, "small vectors use diff_dot_");
+    double res = 0.0, acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    constexpr int NB = N / 8;
+#pragma unroll
+    for (int b8 = 0; b8 < NB; ++b8)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] += d[8 * b8 + u] * d[8 * b8 + u];
+    res += acc[0] + acc[4];
+    res += acc[1] + acc[5];
+    res += acc[2] + acc[6];
+    res += acc[3] + acc[7];
+#pragma unroll
+    for (int i = 8 * NB; i < N; ++i) res += d[i] * d[i];
+    return res;
+}
+
+/*
+ * SysThreeBody18 (ode_systems.cuh; order of operations as defined there and in the test oracle,
+ * threebody18_rhs) dealt out to three lanes. Lane `role` owns body `role`: local components
+ * 0..2 = its position (global 3 role + c), 3..5 = its velocity (global 9 + 3 role + c), and evaluates
+ * ONE of the three pairs: role 0 the pair (0,1), role 1 the pair (1,2), role 2 the pair (0,2), so the
+ * other body's position is always the next lane's. The oracle visits the pairs in the order
+ * (0,1),(0,2),(1,2) and accumulates, per body,
+ *     body 0: (0 + A01) + A02      body 1: (0 - B01) + A12      body 2: (0 - B02) - B12
+ * with A = (p[b] inv) d, B = (p[a] inv) d, d = r_b - r_a, inv = 1 / (|d|^2 |d|) of the pair (a,b): each
+ * lane has one of its two terms and receives the other from the previous lane.
+ */
+struct SplitThreeBody18 {
+    static constexpr int G = 3, NS = 6, FULL = 18, NP = 3;
+    static constexpr bool HAS_SOLOUT = false;
+    ODE_DEV static int gcomp(unsigned role, int c) { return c < 3 ? 3 * (int)role + c : 9 + 3 * (int)role + (c - 3); }
+    /* the index order of the full state as (owner, first local component) runs of three */
+    static constexpr int NSEG = 6, SEGLEN = 3;
+    ODE_DEV static constexpr unsigned seg_owner(int s) { return (unsigned)(s % 3); }
+    ODE_DEV static constexpr int seg_lo(int s) { return (s / 3) * 3; }
+    /* the two parameters a lane needs: pl[0] = p[a], pl[1] = p[b] of its pair (a,b) */
+    ODE_DEV static int par_a(unsigned role) { return role == 1u ? 1 : 0; }
+    ODE_DEV static int par_b(unsigned role) { return role == 0u ? 1 : 2; }
+
+    template <class M>
+    ODE_DEV static void rhs(const Lane3& L, double, const double (&y)[NS], double (&dy)[NS], const double (&pl)[2], M& m) {
+        const bool r0 = L.role == 0u, r1 = L.role == 1u, r2 = L.role == 2u;
+        /* d = r_b - r_a: the next lane's position minus mine, except for role 2, which owns body b = 2 */
+        const double dx = neg_if_(shfl_d_(y[0], L.next) - y[0], r2);
+        const double dyy = neg_if_(shfl_d_(y[1], L.next) - y[1], r2);
+        const double dz = neg_if_(shfl_d_(y[2], L.next) - y[2], r2);
+        const double rr = dx * dx + dyy * dyy + dz * dz;
+        const double r = m.sqrt_nz(rr);
+        const double inv = m.div_nz(1.0, rr * r);
+        const double fa = pl[1] * inv, fb = pl[0] * inv;
+        const double d[3] = {dx, dyy, dz};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double A = fa * d[c], B = fb * d[c];
+            const double recv = shfl_d_(r2 ? A : B, L.prev); /* role 2 hands A02 to role 0; roles 0, 1 hand B01, B12 on */
+            const double u = r0 ? A : neg_if_(r1 ? recv : B, true);
+            const double w = r0 ? recv : (r1 ? A : neg_if_(recv, true));
+            dy[c] = y[3 + c];
+            dy[3 + c] = (0.0 + u) + w;
+        }
+    }
+};
+
+/* sum over the FULL state in index order of per-component terms held by their owners: s = (..((0 + t_0) + t_1)..)
+ * handed from owner to owner; every lane of the group returns the same bits */
+template <class SS>
+ODE_DEV void ordered_sum2_(const Lane3& L, const double (&t1)[SS::NS], const double (&t2)[SS::NS], double& s1, double& s2) {
+    s1 = 0.0;
+    s2 = 0.0;
+    static_for<0, SS::NSEG>([&](auto S) {
+        constexpr int sg = decltype(S)::value;
+        constexpr int lo = SS::seg_lo(sg);
+        double a = s1, b = s2;
+#pragma unroll
+        for (int i = 0; i < SS::SEGLEN; ++i) {
+            a += t1[lo + i];
+            b += t2[lo + i];
+        }
+        s1 = shfl_d_(a, L.base + SS::seg_owner(sg));
+        s2 = shfl_d_(b, L.base + SS::seg_owner(sg));
+    });
+}
+template <class SS>
+ODE_DEV double ordered_sum_(const Lane3& L, const double (&t)[SS::NS]) {
+    double s = 0.0;
+    static_for<0, SS::NSEG>([&](auto S) {
+        constexpr int sg = decltype(S)::value;
+        constexpr int lo = SS::seg_lo(sg);
+        double a = s;
+#pragma unroll
+        for (int i = 0; i < SS::SEGLEN; ++i) a += t[lo + i];
+        s = shfl_d_(a, L.base + SS::seg_owner(sg));
+    });
+    return s;
+}
+/* every lane gets the full vector (index order) of a distributed one: the rare stiffness test only */
+template <class SS>
+ODE_DEV void gather_full_(const Lane3& L, const double (&loc)[SS::NS], double (&full)[SS::FULL]) {
+    static_for<0, SS::NSEG>([&](auto S) {
+        constexpr int sg = decltype(S)::value;
+#pragma unroll
+        for (int i = 0; i < SS::SEGLEN; ++i)
+            full[sg * SS::SEGLEN + i] = shfl_d_(loc[SS::seg_lo(sg) + i], L.base + SS::seg_owner(sg));
+    });
+}
+
+/* ============================================================================ Dop853, three lanes per trajectory */
+template <class SS, int OUT>
+struct Dop853SplitStepper {
+    static constexpr int N = SS::NS, NF = SS::FULL;
+    static constexpr bool DENSE = OUT == ODE_B200_OUT_DENSE;
+    static constexpr bool CONT8 = OUT == ODE_B200_OUT_CONTINUOUS8;
+    static constexpr int kThreads = (DENSE || CONT8) ? 256 : ODE_B200_LOCK_THREADS; /* as the n = 6 lockstep kernels */
+    static constexpr int kSlotsPerWarp = 10;
+    static constexpr int kRefillIdle = ODE_B200_REFILL_IDLE;
+    static_assert(!SS::HAS_SOLOUT, "solout of a split system is not implemented");
+
+    struct State {
+        double y[N], k0[N];
+        double pl[2];
+        double x, h, x_old, h_old, xd;
+        CtrlState ctrl;
+        Counters c;
+        unsigned iasti, non_stiff, stiff_ctr;
+        long long traj;
+    };
+
+    /* ---- result stores (per lane; no shuffles) */
+    ODE_DEV static void push(const KernelArgs& a, State& s, const Lane3& L, double x, const double (&y)[N]) {
+        if (a.out.out_x != nullptr && (long long)s.c.out_count < a.out.out_cap) {
+            const size_t q = (size_t)s.traj * (size_t)a.out_pitch + s.c.out_count;
+            if (L.role == 0u) a.out.out_x[q] = x;
+            double* dst = a.out.out_y + q * NF;
+#pragma unroll
+            for (int c = 0; c < N; ++c) dst[SS::gcomp(L.role, c)] = y[c];
+        }
+        ++s.c.out_count;
+    }
+    ODE_DEV static void push_com(const KernelArgs& a, State& s, const Lane3& L, double brk, double step,
+                                 const double (&rc)[8][N]) {
+        const ode_b200_outputs& o = a.out;
+        if (o.com_break != nullptr && (long long)s.c.com_count < o.com_cap) {
+            const size_t q = (size_t)s.traj * (size_t)a.com_pitch + s.c.com_count;
+            if (L.role == 0u) {
+                o.com_break[q] = brk;
+                o.com_step[q] = step;
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c < N; ++c) o.com_coef[(q * 8 + r) * NF + SS::gcomp(L.role, c)] = rc[r][c];
+        }
+        s.c.com_count += 1;
+    }
+    ODE_DEV static void finish(State& s, const KernelArgs& a, const Lane3& L, int status) {
+        const ode_b200_outputs& o = a.out;
+        const long long t = s.traj;
+        if (status == ODE_B200_OK && ((o.out_cap > 0 && (long long)s.c.out_count > o.out_cap) ||
+                                      (o.com_cap > 0 && (long long)s.c.com_count > o.com_cap)))
+            status = ODE_B200_OUTPUT_CAPACITY_EXCEEDED;
+        if (o.y_final)
+#pragma unroll
+            for (int c = 0; c < N; ++c) o.y_final[(size_t)SS::gcomp(L.role, c) * a.n_traj + t] = s.y[c];
+        if (L.role == 0u) {
+            if (o.x_final) o.x_final[t] = s.x;
+            if (o.h_next) o.h_next[t] = s.h_old;
+            if (o.num_eval) o.num_eval[t] = s.c.num_eval;
+            if (o.accepted) o.accepted[t] = s.c.accepted;
+            if (o.rejected) o.rejected[t] = s.c.rejected;
+            if (o.n_step) o.n_step[t] = s.c.n_step;
+            if (o.status) o.status[t] = status;
+            if (o.out_count) o.out_count[t] = s.c.out_count;
+            if (o.com_count) o.com_count[t] = s.c.com_count;
+            if (o.com_lower) o.com_lower[t] = CONT8 ? a.cfg.x0 : 0.0;
+        }
+    }
+
+    /* compute_y_out, dop853.rs:546-559 */
+    ODE_DEV static void y_out(const double (&rc)[8][N], double th, double th1, double (&o)[N]) {
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            o[i] = rc[0][i] +
+                   (rc[1][i] +
+                    (rc[2][i] +
+                     (rc[3][i] + (rc[4][i] + (rc[5][i] + (rc[6][i] + rc[7][i] * th) * th1) * th) * th1) * th) *
+                        th1) *
+                       th;
+    }
+
+    /* ---- right-hand side with its own check, executed by the whole warp: `use` marks the lanes whose
+     * result will be used (only their flags may force the exact recomputation) */
+    struct RhsIn {
+        double y[N], pl[2], x;
+    };
+    static __device__ __noinline__ void rhs_exact(const Lane3* L, const RhsIn* in, double* dy) {
+        MathExact m;
+        double d[N];
+        SS::rhs(*L, in->x, in->y, d, in->pl, m);
+#pragma unroll
+        for (int i = 0; i < N; ++i) dy[i] = d[i];
+    }
+    ODE_DEV static void rhs_checked(const Lane3& L, bool use, double x, const double (&y)[N], double (&dy)[N],
+                                    const double (&pl)[2]) {
+        MathFast m;
+        SS::rhs(L, x, y, dy, pl, m);
+        if (__builtin_expect(__any_sync(kFullMask, use && m.bad()), 0)) {
+            RhsIn in;
+            double d[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) in.y[i] = y[i];
+            in.pl[0] = pl[0];
+            in.pl[1] = pl[1];
+            in.x = x;
+            rhs_exact(&L, &in, d);
+#pragma unroll
+            for (int i = 0; i < N; ++i) dy[i] = d[i];
+        }
+    }
+
+    /* ---- hinit (dop853.rs:195-251), norms in index order over the full state; whole warp */
+    ODE_DEV static double hinit(const KernelArgs& a, const Lane3& L, double x, const double (&y)[N], const double (&pl)[2]) {
+        double f0[N], f1[N], y1[N], t0[N], t1[N];
+        MathExact mx;
+        SS::rhs(L, x, y, f0, pl, mx);
+        const double posneg = sign_(1.0, a.cfg.x_end - x);
+        const double rtol = a.cfg.rtol, atol = a.cfg.atol;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double sci = atol + fabs(y[i]) * rtol;
+            const double qy = y[i] / sci, qf = f0[i] / sci;
+            t0[i] = qy * qy;
+            t1[i] = qf * qf;
+        }
+        double d0, d1;
+        ordered_sum2_<SS>(L, t0, t1, d0, d1);
+        double h0 = (d0 < 1.0e-10 || d1 < 1.0e-10) ? 1.0e-6 : 0.01 * sqrt(d0 / d1);
+        h0 = fmin(h0, a.h_max_abs);
+        h0 = sign_(h0, posneg);
+#pragma unroll
+        for (int i = 0; i < N; ++i) y1[i] = y[i] + f0[i] * h0;
+        SS::rhs(L, x + h0, y1, f1, pl, mx);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double sci = atol + fabs(y[i]) * rtol;
+            const double q = (f1[i] - f0[i]) / sci;
+            t0[i] = q * q;
+        }
+        double d2 = ordered_sum_<SS>(L, t0);
+        d2 = sqrt(d2) / h0;
+        double h1;
+        if (fmax(sqrt(d1), fabs(d2)) <= 1.0E-15)
+            h1 = fmax(1.0E-6, fabs(h0) * 1.0E-3);
+        else
+            h1 = pow_d(0.01 / fmax(sqrt(d1), d2), 0.125); /* second d2 without abs, as in the source */
+        return sign_(fmin(100.0 * fabs(h0), fmin(h1, a.h_max_abs)), posneg);
+    }
+
+    /* ---- prologue of the trajectories the lanes with `ok` have just claimed (dop853.rs:255-278); whole warp */
+    ODE_DEV static void init_all(State& s, const KernelArgs& a, long long t, bool ok, const Lane3& L) {
+        const long long tt = ok ? t : 0; /* lanes that commit nothing still load from a valid row */
+        double y[N], pl[2], k0[N];
+#pragma unroll
+        for (int c = 0; c < N; ++c) y[c] = __ldg(a.y0 + (size_t)SS::gcomp(L.role, c) * a.n_traj + tt);
+        const int ia = SS::par_a(L.role), ib = SS::par_b(L.role);
+        pl[0] = a.params_per_traj ? __ldg(a.params + (size_t)ia * a.n_traj + tt) : __ldg(a.params + ia);
+        pl[1] = a.params_per_traj ? __ldg(a.params + (size_t)ib * a.n_traj + tt) : __ldg(a.params + ib);
+        const double x = a.cfg.x0;
+        double h = a.cfg.h0;
+        unsigned num_eval = 0;
+        if (h == 0.0) { /* batch-uniform */
+            h = hinit(a, L, x, y, pl);
+            num_eval += 2;
+        }
+        rhs_checked(L, ok, x, y, k0, pl);
+        num_eval += 1;
+        if (ok) {
+            s.traj = t;
+#pragma unroll
+            for (int c = 0; c < N; ++c) {
+                s.y[c] = y[c];
+                s.k0[c] = k0[c];
+            }
+            s.pl[0] = pl[0];
+            s.pl[1] = pl[1];
+            s.x = s.x_old = s.xd = x;
+            counters_init_<false>(s.c);
+            s.c.num_eval = num_eval;
+            ctrl_init_(s.ctrl, a);
+            s.iasti = s.non_stiff = s.stiff_ctr = 0;
+            s.h = h;
+            s.h_old = h;
+            /* solution_output(y0), dop853.rs:273-274 -> :515-519 / :541 */
+            push(a, s, L, x, y);
+            if constexpr (DENSE) s.xd += a.cfg.dx; /* first call: |xd - x0| = 0 < EPSILON always */
+        }
+    }
+
+    struct Work {
+        double k[12][N]; /* k[0] = f(x, y); k[s] = stage s + 1 */
+        double ynext[N]; /* argument of stage 12 (stiffness test) */
+        double y8[N];    /* 8th-order solution */
+        double knew[N];  /* f(x + h, y8): the reference evaluates it after accepting (dop853.rs:366); here it is
+                            part of the warp-uniform block and simply unused by a rejected attempt */
+        double err;
+        CtrlEval ce;
+    };
+    struct ColdIn {
+        double y[N], k0[N], pl[2], x, h, pw_old;
+    };
+
+    /* the straight-line block of one attempt; whole warp. Same statements per component as
+     * Dop853Stepper::core (ode_kernels.cuh) */
+    template <class M>
+    ODE_DEV static void core(const Lane3& L, const double (&y)[N], const double (&k0)[N], const double (&pl)[2],
+                             double pw_old, const KernelArgs& a, double x, double h, Work& w, M& m) {
+        const ode_b200_config& cfg = a.cfg;
+        double(&k)[12][N] = w.k;
+        double(&ynext)[N] = w.ynext;
+        double(&y8)[N] = w.y8;
+        bool bad = false;
+#pragma unroll
+        for (int i = 0; i < N; ++i) k[0][i] = k0[i];
+        static_for<1, 12>([&](auto S) {
+            constexpr int sg = decltype(S)::value;
+#pragma unroll
+            for (int i = 0; i < N; ++i) ynext[i] = y[i];
+            double hs = h;
+            asm volatile("" : "+d"(hs)); /* see Dop853Stepper::core */
+            static_for<0, sg>([&](auto J) {
+                constexpr int j = decltype(J)::value;
+                constexpr double aij = TabDp8::a(sg, j);
+                if constexpr (aij != 0.0) {
+                    const double ha = hs * c_dp8_a[sg][j];
+#pragma unroll
+                    for (int i = 0; i < N; ++i) ynext[i] = ynext[i] + k[j][i] * ha;
+                }
+            });
+            SS::rhs(L, x + (h * c_dp8_c[sg]), ynext, k[sg], pl, m);
+            if constexpr (sg >= 1 && sg <= 4) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) bad |= nonfinite_(k[sg][i]);
+            }
+        });
+        double bsum[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            bsum[i] = ((((((k[0][i] * c_dp8_b[0] + k[5][i] * c_dp8_b[5]) + k[6][i] * c_dp8_b[6]) +
+                          k[7][i] * c_dp8_b[7]) +
+                         k[8][i] * c_dp8_b[8]) +
+                        k[9][i] * c_dp8_b[9]) +
+                       k[10][i] * c_dp8_b[10]) +
+                      k[11][i] * c_dp8_b[11];
+            y8[i] = y[i] + bsum[i] * h;
+        }
+        SS::rhs(L, x + h, y8, w.knew, pl, m);
+        double t1[N], t2[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double ee = k[0][i] * c_dp8_e[0];
+            ee = ee + k[5][i] * c_dp8_e[5];
+            ee = ee + k[6][i] * c_dp8_e[6];
+            ee = ee + k[7][i] * c_dp8_e[7];
+            ee = ee + k[8][i] * c_dp8_e[8];
+            ee = ee + k[9][i] * c_dp8_e[9];
+            ee = ee + k[10][i] * c_dp8_e[10];
+            ee = ee + k[11][i] * c_dp8_e[11];
+            const double eb = ((bsum[i] - k[0][i] * c_dp8_bhh[0]) - k[8][i] * c_dp8_bhh[1]) -
+                              k[11][i] * c_dp8_bhh[2];
+            const double sc = cfg.atol + fmax(fabs(y[i]), fabs(y8[i])) * cfg.rtol;
+            bad |= nonfinite_(y8[i]);
+            const double rsc = m.rcp(sc);
+            const double q1 = m.div_by(ee, sc, rsc), q2 = m.div_by(eb, sc, rsc);
+            t1[i] = q1 * q1;
+            t2[i] = q2 * q2;
+        }
+        double err, err2;
+        ordered_sum2_<SS>(L, t1, t2, err, err2); /* err += ..., err2 += ... over i = 0..n-1 (dop853.rs:349-356) */
+        double deno = err + 0.01 * err2;
+        if (deno <= 0.0) deno = 1.0;
+        err = fabs(h) * err * m.sqrt_nz(m.div_nz(1.0, deno * (double)NF));
+        if (group_any_(L, bad)) err = qnan_();
+        w.err = err;
+        ctrl_eval_(pw_old, a, err, h, m, w.ce);
+    }
+
+    static __device__ __noinline__ void core_exact(const Lane3* L, const ColdIn* in, const KernelArgs* a, Work* w) {
+        MathExact m;
+        core<MathExact>(*L, in->y, in->k0, in->pl, in->pw_old, *a, in->x, in->h, *w, m);
+    }
+
+    /* the three extra stages of the dense output (dop853.rs:414-454); whole warp */
+    struct DenseIn {
+        double y[N], pl[2], p15[N], p16[N], yy[N], x, h;
+    };
+    template <class M>
+    ODE_DEV static void dense_stages(const Lane3& L, const double (&y)[N], const double (&pl)[2], const double (&yy0)[N],
+                                     const double (&p15)[N], const double (&p16)[N], double x, double h, double (&k14)[N],
+                                     double (&k15)[N], double (&k16)[N], M& m) {
+        double yy[N];
+        SS::rhs(L, x + h * c_dp8_c[13], yy0, k14, pl, m);
+#pragma unroll
+        for (int i = 0; i < N; ++i) yy[i] = y[i] + (p15[i] + k14[i] * c_dp8_a[14][13]) * h;
+        SS::rhs(L, x + h * c_dp8_c[14], yy, k15, pl, m);
+#pragma unroll
+        for (int i = 0; i < N; ++i) yy[i] = y[i] + ((p16[i] + k14[i] * c_dp8_a[15][13]) + k15[i] * c_dp8_a[15][14]) * h;
+        SS::rhs(L, x + h * c_dp8_c[15], yy, k16, pl, m);
+    }
+    static __device__ __noinline__ void dense_stages_exact(const Lane3* L, const DenseIn* in, double* k14, double* k15,
+                                                           double* k16) {
+        MathExact m;
+        double a14[N], a15[N], a16[N];
+        dense_stages<MathExact>(*L, in->y, in->pl, in->yy, in->p15, in->p16, in->x, in->h, a14, a15, a16, m);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            k14[i] = a14[i];
+            k15[i] = a15[i];
+            k16[i] = a16[i];
+        }
+    }
+
+    /* one pass of `while !last` (dop853.rs:281-510) for every lane of the warp; `active` lanes hold a trajectory */
+    ODE_DEV static void attempt_all(State& s, const KernelArgs& a, bool& active, const Lane3& L) {
+        const ode_b200_config& cfg = a.cfg;
+        /* ---- per lane: the two abort tests and the clamp of the last step */
+        bool go = active, last = false;
+        if (active) {
+            int fin = -1;
+            if (s.c.n_step >= cfg.n_max)
+                fin = ODE_B200_MAX_NUM_STEP_REACHED;
+            else if (0.1 * fabs(s.h) <= cfg.uround * fabs(s.x))
+                fin = ODE_B200_STEP_SIZE_UNDERFLOW;
+            if (fin >= 0) {
+                s.h_old = s.h;
+                finish(s, a, L, fin);
+                active = go = false;
+            } else {
+                if ((s.x + 1.01 * s.h - cfg.x_end) * a.posneg > 0.0) {
+                    s.h = cfg.x_end - s.x;
+                    last = true;
+                }
+                s.c.n_step += 1;
+            }
+        }
+        if (!__any_sync(kFullMask, go)) return;
+        const double h = s.h, x = s.x;
+
+        /* ---- whole warp: the attempt */
+        Work w;
+        MathFast m;
+        core<MathFast>(L, s.y, s.k0, s.pl, s.ctrl.pw_old, a, x, h, w, m);
+        if (__builtin_expect(__any_sync(kFullMask, go && m.bad()), 0)) {
+            ColdIn in;
+            Work w2;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                in.y[i] = s.y[i];
+                in.k0[i] = s.k0[i];
+            }
+            in.pl[0] = s.pl[0];
+            in.pl[1] = s.pl[1];
+            in.x = x;
+            in.h = h;
+            in.pw_old = s.ctrl.pw_old;
+            core_exact(&L, &in, &a, &w2);
+            w = w2;
+        }
+        double(&k)[12][N] = w.k;
+        double(&y8)[N] = w.y8;
+        double(&knew)[N] = w.knew;
+
+        /* ---- per lane: controller */
+        double h_new = 0.0;
+        bool acc = false;
+        if (go) {
+            s.c.num_eval += 11;
+            acc = ctrl_commit_(s.ctrl, a, w.ce, w.err, h, h_new);
+            if (acc) {
+                s.c.accepted += 1;
+                s.c.num_eval += 1; /* knew */
+            } else {
+                if (s.c.accepted >= 1) s.c.rejected += 1;
+                s.h = h_new;
+            }
+        }
+        /* ---- stiffness detection (dop853.rs:372-396): rare, whole warp when any lane is due */
+        bool due = false;
+        if (acc) {
+            if (++s.stiff_ctr == cfg.n_stiff) s.stiff_ctr = 0;
+            due = s.stiff_ctr == 0 || s.iasti > 0;
+        }
+        if (__builtin_expect(__any_sync(kFullMask, due), 0)) {
+            double d1[N], d2[N], f1[NF], f2[NF];
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                d1[i] = knew[i] - k[11][i];
+                d2[i] = y8[i] - w.ynext[i];
+            }
+            gather_full_<SS>(L, d1, f1);
+            gather_full_<SS>(L, d2, f2);
+            if (due) {
+                const double num = sq_dot_<NF>(f1), den = sq_dot_<NF>(f2);
+                const double h_lamb = den > 0.0 ? h * sqrt(num / den) : 0.0;
+                if (h_lamb > 6.1) {
+                    s.non_stiff = 0;
+                    s.iasti += 1;
+                    if (s.iasti == 15) {
+                        s.h_old = h;
+                        finish(s, a, L, ODE_B200_STIFFNESS_DETECTED);
+                        active = acc = false;
+                    }
+                } else {
+                    s.non_stiff += 1;
+                    if (s.non_stiff == 6) s.iasti = 0;
+                }
+            }
+        }
+
+        /* ---- dense-output coefficients (dop853.rs:398-480): whole warp when any lane accepted */
+        double rc[8][N];
+        if constexpr (DENSE || CONT8) {
+            if (__any_sync(kFullMask, acc)) {
+                double yy[N], p15[N], p16[N], k14[N], k15[N], k16[N];
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    rc[0][i] = s.y[i];
+                    const double ydiff = y8[i] - s.y[i];
+                    rc[1][i] = ydiff;
+                    const double bspl = k[0][i] * h - ydiff;
+                    rc[2][i] = bspl;
+                    rc[3][i] = (ydiff - knew[i] * h) - bspl;
+                    const double k0 = k[0][i], k5 = k[5][i], k6 = k[6][i], k7 = k[7][i], k8 = k[8][i], k9 = k[9][i],
+                                 k10 = k[10][i], k11 = k[11][i], kn = knew[i];
+                    static_for<0, 4>([&](auto R) {
+                        constexpr int r = decltype(R)::value;
+                        double v = 0.0 + k0 * c_dp8_d[r][0];
+                        v = v + k5 * c_dp8_d[r][5];
+                        v = v + k6 * c_dp8_d[r][6];
+                        v = v + k7 * c_dp8_d[r][7];
+                        v = v + k8 * c_dp8_d[r][8];
+                        v = v + k9 * c_dp8_d[r][9];
+                        v = v + k10 * c_dp8_d[r][10];
+                        v = v + k11 * c_dp8_d[r][11];
+                        rc[4 + r][i] = v;
+                    });
+                    yy[i] = s.y[i] + (((((((k0 * c_dp8_a[13][0] + k6 * c_dp8_a[13][6]) + k7 * c_dp8_a[13][7]) +
+                                           k8 * c_dp8_a[13][8]) +
+                                          k9 * c_dp8_a[13][9]) +
+                                         k10 * c_dp8_a[13][10]) +
+                                        k11 * c_dp8_a[13][11]) +
+                                       kn * c_dp8_a[13][12]) *
+                                          h;
+                    p15[i] = (((((k0 * c_dp8_a[14][0] + k5 * c_dp8_a[14][5]) + k6 * c_dp8_a[14][6]) +
+                                k7 * c_dp8_a[14][7]) +
+                               k10 * c_dp8_a[14][10]) +
+                              k11 * c_dp8_a[14][11]) +
+                             kn * c_dp8_a[14][12];
+                    p16[i] = ((((k0 * c_dp8_a[15][0] + k5 * c_dp8_a[15][5]) + k6 * c_dp8_a[15][6]) +
+                               k7 * c_dp8_a[15][7]) +
+                              k8 * c_dp8_a[15][8]) +
+                             kn * c_dp8_a[15][12];
+                }
+                MathFast md;
+                dense_stages<MathFast>(L, s.y, s.pl, yy, p15, p16, x, h, k14, k15, k16, md);
+                if (__builtin_expect(__any_sync(kFullMask, acc && md.bad()), 0)) {
+                    DenseIn in;
+                    double e14[N], e15[N], e16[N];
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        in.y[i] = s.y[i];
+                        in.p15[i] = p15[i];
+                        in.p16[i] = p16[i];
+                        in.yy[i] = yy[i];
+                    }
+                    in.pl[0] = s.pl[0];
+                    in.pl[1] = s.pl[1];
+                    in.x = x;
+                    in.h = h;
+                    dense_stages_exact(&L, &in, e14, e15, e16);
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        k14[i] = e14[i];
+                        k15[i] = e15[i];
+                        k16[i] = e16[i];
+                    }
+                }
+                if (acc) s.c.num_eval += 3;
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    const double kn = knew[i], ka = k14[i], kb = k15[i], kc = k16[i];
+                    static_for<0, 4>([&](auto R) {
+                        constexpr int r = decltype(R)::value;
+                        rc[4 + r][i] = ((((rc[4 + r][i] + kn * c_dp8_d[r][12]) + ka * c_dp8_d[r][13]) +
+                                         kb * c_dp8_d[r][14]) +
+                                        kc * c_dp8_d[r][15]) *
+                                       h;
+                    });
+                }
+            }
+        }
+
+        /* ---- per lane: commit the accepted step, outputs, exit */
+        if (acc) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                s.k0[i] = knew[i];
+                s.y[i] = y8[i];
+            }
+            s.x_old = x;
+            s.x = x + h;
+            s.h_old = h;
+            if constexpr (DENSE) { /* solution_output(k[4]), dop853.rs:515-539 */
+                double yo[N];
+                if (fabs(s.xd - cfg.x0) < 2.220446049250313e-16) {
+                    push(a, s, L, cfg.x0, s.y);
+                    s.xd += cfg.dx;
+                } else {
+                    bool unsupported = false;
+                    const double rh = div_rcp_(s.h_old);
+                    const bool h_ok = div_in_range_(s.h_old);
+                    while (fabs(s.xd) <= fabs(s.x)) {
+                        if (fabs(s.x_old) <= fabs(s.xd) && fabs(s.x) >= fabs(s.xd)) {
+                            const double th = div_with_rcp_(s.xd - s.x_old, s.h_old, rh, h_ok), th1 = 1.0 - th;
+                            y_out(rc, th, th1, yo);
+                            push(a, s, L, s.xd, yo);
+                            s.xd += cfg.dx;
+                            if (s.c.out_count > (1u << 26)) { unsupported = true; break; }
+                        } else { /* the reference never leaves this loop */
+                            unsupported = true;
+                            break;
+                        }
+                    }
+                    if (unsupported) {
+                        finish(s, a, L, ODE_B200_UNSUPPORTED_DOMAIN);
+                        active = false;
+                        return;
+                    }
+                    if (fabs(s.xd - cfg.x_end) < 1.0e-9) {
+                        const double th = div_with_rcp_(cfg.x_end - s.x_old, s.h_old, rh, h_ok), th1 = 1.0 - th;
+                        y_out(rc, th, th1, yo);
+                        push(a, s, L, cfg.x_end, yo);
+                        s.xd += cfg.dx;
+                    }
+                }
+            } else if constexpr (CONT8) {
+                push(a, s, L, s.x, s.y);
+                push_com(a, s, L, fabs(s.x), s.h_old, rc);
+            } else {
+                push(a, s, L, cfg.x0, s.y); /* pushes x0, not x (Q6) */
+            }
+            if (last) { /* dop853.rs:499-502 */
+                s.h_old = a.posneg * h_new;
+                finish(s, a, L, ODE_B200_OK);
+                active = false;
+                return;
+            }
+            s.h = h_new;
+        }
+    }
+};
+
+/* ---- lane scheduler of the split steppers: run_lanes_ (ode_device.cuh) with groups of three lanes
+ * claiming one trajectory, and every shuffle-bearing phase executed by whole warps */
+template <class Stepper>
+ODE_DEV void run_lanes_split_(const KernelArgs& a) {
+    stage_tables_();
+    Lane3 L;
+    L.init();
+    typename Stepper::State st;
+    st.traj = 0;
+    st.c.out_count = 0;
+    st.x = st.h = st.x_old = st.h_old = st.xd = 0.0;
+    st.pl[0] = st.pl[1] = 1.0;
+#pragma unroll
+    for (int i = 0; i < Stepper::N; ++i) st.y[i] = st.k0[i] = 1.0 + (double)i + (double)L.role; /* never read as results */
+    ctrl_init_(st.ctrl, a);
+    counters_init_<false>(st.c);
+    st.iasti = st.non_stiff = st.stiff_ctr = 0;
+    bool active = false, exhausted = !L.valid, first = true, refilled = false;
+    int idle_acc = 0, idle_prev = 0;
+    unsigned pass = 0;
+    constexpr int kRefillRamp = ODE_B200_REFILL_RAMP;
+    constexpr int group = Stepper::kThreads / 32 * 30; /* working lanes of the CTA */
+    constexpr unsigned sync_every = ODE_B200_SYNC_EVERY;
+    constexpr unsigned kLeaders = 0x09249249u; /* lanes 0, 3, ..., 27: one per group */
+    const unsigned warp = threadIdx.x >> 5, slot = L.base / 3u;
+    for (;;) {
+        if (pass % sync_every == 0) {
+            const int n_active = __syncthreads_count(active);
+            if (n_active == 0 && refilled) break;
+            const int idle = group - n_active;
+            idle_acc += idle * (int)sync_every;
+            refilled = n_active == 0 || (idle_acc >= Stepper::kRefillIdle && kRefillRamp * (idle - idle_prev) <= idle);
+            idle_prev = refilled ? 0 : idle;
+            if (refilled) idle_acc = 0;
+            const bool want = refilled && !active && !exhausted;
+            const unsigned need = idle == 0 ? 0u : __ballot_sync(kFullMask, want);
+            if (need) {
+                const unsigned need0 = need & kLeaders;
+                long long idx;
+                if (a.use_queue) {
+                    const int leader = __ffs(need0) - 1;
+                    unsigned long long b = 0;
+                    if ((int)(threadIdx.x & 31u) == leader) b = atomicAdd(a.queue, (unsigned long long)__popc(need0));
+                    b = __shfl_sync(kFullMask, b, leader);
+                    idx = (long long)b + __popc(need0 & ((1u << L.base) - 1u));
+                } else {
+                    idx = first ? ((long long)blockIdx.x * (Stepper::kThreads / 32) + warp) * Stepper::kSlotsPerWarp + slot
+                                : a.n_traj;
+                }
+                const bool ok = want && idx < a.n_traj;
+                if (want && !ok) exhausted = true;
+                Stepper::init_all(st, a, idx, ok, L);
+                if (ok) active = true;
+                first = false;
+            }
+            if (refilled) __syncthreads();
+        }
+        if (__any_sync(kFullMask, active)) Stepper::attempt_all(st, a, active, L);
+        ++pass;
+    }
+}
+
+template <class Stepper>
+__global__ void __launch_bounds__(Stepper::kThreads, 1) ode_split_step_loop_kernel(const __grid_constant__ KernelArgs a) {
+    run_lanes_split_<Stepper>(a);
+}
+
+}  // namespace ode_b200

@@ -122,7 +122,8 @@ def test_continuous_with_samples_but_without_model_capacity(system, method, out_
         cfg = ob.config_new(method, 0.0, 2.0, 0.1, 1e-6, 1e-6, out_type=out_type)
     g, o = run_both(system, cfg, y0, p, out_cap=400, com_cap=0)
     assert_same_outputs(g, o, "%s continuous, com_cap=0" % system)
-    assert (g.com_count == g.accepted).all() and (g.out_count > 1).all()
+    ok = g.status == ob.OK  # an IntegrationError leaves the loop before the last step's interval is added
+    assert ok.any() and (g.com_count[ok] == g.accepted[ok]).all() and (g.out_count > 1).all()
     g2, o2 = run_both(system, cfg, y0, p, out_cap=400, com_cap=400)  # and the recorded model still agrees
     assert_same_outputs(g2, o2, "%s continuous, com_cap=400" % system)
 

@@ -79,6 +79,8 @@ def main():
     reps = int(os.environ.get("KBENCH_REPS", 3))
     peak, _ = ob.measure_fp64_peak(0)
     ctx = ob.default_context(0)
+    if os.environ.get("KBENCH_NOSPLIT"):
+        ctx.set_lane_split(False)
     for q in (1, 0) if os.environ.get("KBENCH_STATIC") else (1,):
         ctx.set_work_queue(bool(q))
         for name in names:
