@@ -110,7 +110,7 @@ def test_continuous_with_samples_but_without_model_capacity(system, method, out_
     sized the dynamic shared memory without it)."""
     if system == "test_exp":
         y0, p = np.linspace(0.5, 1.5, 300).reshape(1, -1), None
-        cfg = ob.config_new(method, 0.0, 1.0, 0.1, 1e-8, 1e-8, out_type=out_type)
+        cfg = ob.config_new(method, 0.0, 1.0, 0.1, 1e-4, 1e-4, out_type=out_type)
     elif system == "kepler":
         y0, p = W.kepler_sweep(300)
         cfg = ob.config_new(method, 0.0, W.kepler_period(), 60.0, 1e-8, 1e-8, out_type=out_type)

@@ -10,8 +10,13 @@ mkdir -p $ROOT/gpurun_out
 cd $ROOT
 KBENCH_N=$N KBENCH_REPS=1 python tools/kbench.py $WL > gpurun_out/plain_$LABEL.log 2>&1
 # -k regex: the step loop only; -s 0 -c 1: the first launch (kbench runs one with KBENCH_REPS=1)
-KBENCH_N=$N KBENCH_REPS=1 ncu --set full --clock-control none --import-source on -k regex:ode_step_loop -c 1 \
+KBENCH_N=$N KBENCH_REPS=1 ncu --set full --clock-control none --import-source on -k regex:step_loop -c 1 \
     -f -o gpurun_out/$LABEL python tools/kbench.py $WL > gpurun_out/ncu_$LABEL.log 2>&1
 ncu -i gpurun_out/$LABEL.ncu-rep --page raw --csv > gpurun_out/${LABEL}_raw.csv
+if [ -n "$NCU_SOURCE" ]; then  # per-instruction view (SASS + source lines), compressed
+  ncu -i gpurun_out/$LABEL.ncu-rep --page source --csv 2>/dev/null | gzip -9 > gpurun_out/${LABEL}_src.csv.gz
+fi
+# gpurun copies back at most 64 MiB per call: the report itself stays on the box unless asked for
+[ -n "$NCU_KEEP_REP" ] || rm -f gpurun_out/$LABEL.ncu-rep
 python tools/ncu_summary.py $OUT $LABEL=gpurun_out/${LABEL}_raw.csv
 echo "captured $LABEL -> $OUT"
