@@ -400,7 +400,7 @@ static int launch_device(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg
 
     /* large states (ode_split.cuh): Dop853 with one trajectory per group of three lanes */
     const void* split_fn = nullptr;
-    if (!s.jit && cfg->method == ODE_B200_DOP853 && c->lane_split) split_fn = kBuiltins[sys_id]->dop853_split_kernels[cfg->out_type];
+    if (!s.jit && cfg->method == ODE_B200_DOP853 && c->lane_split) split_fn = kBuiltins[sys_id]->dop853_split_kernels[0][cfg->out_type];
     const int block = split_fn ? kBuiltins[sys_id]->split_threads[cfg->out_type]
                                : block_threads_for(s.dim, cfg->method, records_dense(cfg->method, cfg->out_type));
     const long long traj_per_block = split_fn ? (long long)(block / 32) * kBuiltins[sys_id]->split_traj_per_warp : block;
@@ -438,7 +438,14 @@ static int launch_device(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg
         ((ka.com_pitch & 1) != 0 || ((uintptr_t)ka.out.com_break & 15u) != 0 || ((uintptr_t)ka.out.com_step & 15u) != 0 ||
          ((uintptr_t)ka.out.com_coef & 15u) != 0))
         stage = false;
-    const size_t dyn_smem = stage ? (size_t)stage_smem_doubles(s.dim, block, com_m) * sizeof(double) : 0;
+    size_t dyn_smem = stage ? (size_t)stage_smem_doubles(s.dim, block, com_m) * sizeof(double) : 0;
+    if (split_fn && ka.out.out_x != nullptr && ((uintptr_t)ka.out.out_y & 15u) == 0 &&
+        (ka.out.com_break == nullptr || ((uintptr_t)ka.out.com_coef & 15u) == 0)) {
+        /* the split kernels stage recorded results per trajectory slot (whole rows of the result arrays:
+         * 16-byte aligned whenever the arrays are) */
+        split_fn = kBuiltins[sys_id]->dop853_split_kernels[1][cfg->out_type];
+        dyn_smem = (size_t)(block / 32) * kBuiltins[sys_id]->split_traj_per_warp * kBuiltins[sys_id]->split_slot_bytes;
+    }
     CUDA_TRY(cudaMemsetAsync(ka.queue, 0, sizeof(unsigned long long), stream));
     if (stream == c->stream) CUDA_TRY(cudaEventRecord(c->ev0, stream));
     if (!s.jit) {

@@ -37,18 +37,20 @@ const void* rk4_f32_kernel_ptr() {
     extern "C" const ode_b200::SystemEntry ode_b200_entry_##NAME = {                     \
         #NAME, ode_b200::SYS::DIM, ode_b200::SYS::NP, ode_b200::SYS::HAS_SOLOUT ? 1 : 0, \
         {ODE_B200_KSET(SYS, false), ODE_B200_KSET(SYS, true)}, ode_b200::rk4_f32_kernel_ptr<ode_b200::SYS>(), \
-        {nullptr, nullptr, nullptr, nullptr}, {0, 0, 0, 0}, 0};
+        {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}}, {0, 0, 0, 0}, 0, 0};
 
 /* a system that also has a three-lanes-per-trajectory form (ode_split.cuh) for Dop853 */
-#define ODE_B200_SPLIT_KPTR(SPLIT, OUT) \
-    ((const void*)&ode_b200::ode_split_step_loop_kernel<ode_b200::Dop853SplitStepper<ode_b200::SPLIT, OUT>>)
+#define ODE_B200_SPLIT_KPTR(SPLIT, OUT, ST) \
+    ((const void*)&ode_b200::ode_split_step_loop_kernel<ode_b200::Dop853SplitStepper<ode_b200::SPLIT, OUT, ST>>)
 #define ODE_B200_SPLIT_THREADS(SPLIT, OUT) ode_b200::Dop853SplitStepper<ode_b200::SPLIT, OUT>::kThreads
+#define ODE_B200_SPLIT_KSET(SPLIT, ST)                                                                      \
+    {ODE_B200_SPLIT_KPTR(SPLIT, ODE_B200_OUT_DENSE, ST), ODE_B200_SPLIT_KPTR(SPLIT, ODE_B200_OUT_SPARSE, ST), \
+     ODE_B200_SPLIT_KPTR(SPLIT, ODE_B200_OUT_SPARSE, ST), ODE_B200_SPLIT_KPTR(SPLIT, ODE_B200_OUT_CONTINUOUS8, ST)}
 #define ODE_B200_DEFINE_SYSTEM_WITH_SPLIT(SYS, NAME, SPLIT)                                                   \
     extern "C" const ode_b200::SystemEntry ode_b200_entry_##NAME = {                                          \
         #NAME, ode_b200::SYS::DIM, ode_b200::SYS::NP, ode_b200::SYS::HAS_SOLOUT ? 1 : 0,                      \
         {ODE_B200_KSET(SYS, false), ODE_B200_KSET(SYS, true)}, ode_b200::rk4_f32_kernel_ptr<ode_b200::SYS>(), \
-        {ODE_B200_SPLIT_KPTR(SPLIT, ODE_B200_OUT_DENSE), ODE_B200_SPLIT_KPTR(SPLIT, ODE_B200_OUT_SPARSE),     \
-         ODE_B200_SPLIT_KPTR(SPLIT, ODE_B200_OUT_SPARSE), ODE_B200_SPLIT_KPTR(SPLIT, ODE_B200_OUT_CONTINUOUS8)}, \
+        {ODE_B200_SPLIT_KSET(SPLIT, false), ODE_B200_SPLIT_KSET(SPLIT, true)},                                \
         {ODE_B200_SPLIT_THREADS(SPLIT, ODE_B200_OUT_DENSE), ODE_B200_SPLIT_THREADS(SPLIT, ODE_B200_OUT_SPARSE), \
          ODE_B200_SPLIT_THREADS(SPLIT, ODE_B200_OUT_SPARSE), ODE_B200_SPLIT_THREADS(SPLIT, ODE_B200_OUT_CONTINUOUS8)}, \
-        10};
+        10, ode_b200::Dop853SplitStepper<ode_b200::SPLIT, ODE_B200_OUT_SPARSE>::kSlotDoubles * 8};

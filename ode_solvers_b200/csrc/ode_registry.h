@@ -17,9 +17,10 @@ struct SystemEntry {
     const void* rk4_f32_kernel;
     /* Dop853 with one trajectory per group of three lanes (ode_split.cuh), by out_type; nullptr: the
      * system has no split form and runs one trajectory per thread */
-    const void* dop853_split_kernels[4];
+    const void* dop853_split_kernels[2][4]; /* [results staged through shared memory: no, yes][out_type] */
     int split_threads[4];         /* CTA size of each of them */
     int split_traj_per_warp;      /* 10: lanes 30 and 31 stay idle */
+    int split_slot_bytes;         /* shared memory per trajectory slot of a staged launch */
 };
 
 }  // namespace ode_b200

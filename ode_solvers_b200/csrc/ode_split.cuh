@@ -51,9 +51,6 @@ struct Lane3 {
 };
 
 ODE_DEV double shfl_d_(double v, unsigned src) { return __shfl_sync(kFullMask, v, (int)src); }
-ODE_DEV double neg_if_(double v, bool c) { /* exact: a sign flip */
-    return __hiloint2double(__double2hiint(v) ^ (c ? (int)0x80000000 : 0), __double2loint(v));
-}
 /* true for every lane of a group in which any lane holds true */
 ODE_DEV bool group_any_(const Lane3& L, bool b) { return ((__ballot_sync(kFullMask, b) >> L.base) & 7u) != 0u; }
 
@@ -80,12 +77,20 @@ ODE_DEV double sq_dot_(const double (&d)[N]) {
  * SysThreeBody18 (ode_systems.cuh; order of operations as defined there and in the test oracle,
  * threebody18_rhs) dealt out to three lanes. Lane `role` owns body `role`: local components
  * 0..2 = its position (global 3 role + c), 3..5 = its velocity (global 9 + 3 role + c), and evaluates
- * ONE of the three pairs: role 0 the pair (0,1), role 1 the pair (1,2), role 2 the pair (0,2), so the
- * other body's position is always the next lane's. The oracle visits the pairs in the order
- * (0,1),(0,2),(1,2) and accumulates, per body,
- *     body 0: (0 + A01) + A02      body 1: (0 - B01) + A12      body 2: (0 - B02) - B12
- * with A = (p[b] inv) d, B = (p[a] inv) d, d = r_b - r_a, inv = 1 / (|d|^2 |d|) of the pair (a,b): each
- * lane has one of its two terms and receives the other from the previous lane.
+ * ONE of the three pairs, the one of its own body and the NEXT lane's: role 0 the pair (0,1), role 1
+ * the pair (1,2), role 2 the pair (2,0). The oracle visits the pairs (a,b) in the order (0,1),(0,2),(1,2)
+ * with d = r_b - r_a, inv = 1 / (|d|^2 |d|), A = (p[b] inv) d, B = (p[a] inv) d and accumulates, per body,
+ *     body 0: (0 + A01) + A02      body 1: (0 - B01) + A12      body 2: (0 - B02) - B12.
+ * With e = r_next - r_own (= d for roles 0 and 1, = -d for role 2: squares, |d| and inv do not see the
+ * sign, and (f inv)(-d) = -((f inv) d) exactly) every lane computes
+ *     own  = (p[role + 1] inv) e      ( A01 | A12 | -B02 )   the term of its own body
+ *     send = (p[role]     inv) e      ( B01 | B12 | -A02 )   the term the NEXT lane's body needs
+ * receives the previous lane's `send` as recv, and every body's acceleration is (0 + own) - recv:
+ *     body 0: (0 + A01) - (-A02)     body 1: (0 + A12) - B01     body 2: (0 + (-B02)) - B12.
+ * Bit for bit the oracle's values: a - b is a + (-b); and (0 + u) + w == (0 + w) + u for all u, w (IEEE
+ * addition commutes, and adding +0 first only turns a -0 operand into +0, after which either order gives
+ * the same sum, also when both are zeros), which covers body 1's swapped order. No lane-dependent
+ * selection is left: the lanes differ only in the two parameters they were handed at the prologue.
  */
 struct SplitThreeBody18 {
     static constexpr int G = 3, NS = 6, FULL = 18, NP = 3;
@@ -95,30 +100,26 @@ struct SplitThreeBody18 {
     static constexpr int NSEG = 6, SEGLEN = 3;
     ODE_DEV static constexpr unsigned seg_owner(int s) { return (unsigned)(s % 3); }
     ODE_DEV static constexpr int seg_lo(int s) { return (s / 3) * 3; }
-    /* the two parameters a lane needs: pl[0] = p[a], pl[1] = p[b] of its pair (a,b) */
-    ODE_DEV static int par_a(unsigned role) { return role == 1u ? 1 : 0; }
-    ODE_DEV static int par_b(unsigned role) { return role == 0u ? 1 : 2; }
+    /* the two parameters a lane needs: pl[0] = p[role + 1] (own term), pl[1] = p[role] (the term it hands on) */
+    ODE_DEV static int par_a(unsigned role) { return (int)((role + 1u) % 3u); }
+    ODE_DEV static int par_b(unsigned role) { return (int)role; }
 
     template <class M>
     ODE_DEV static void rhs(const Lane3& L, double, const double (&y)[NS], double (&dy)[NS], const double (&pl)[2], M& m) {
-        const bool r0 = L.role == 0u, r1 = L.role == 1u, r2 = L.role == 2u;
-        /* d = r_b - r_a: the next lane's position minus mine, except for role 2, which owns body b = 2 */
-        const double dx = neg_if_(shfl_d_(y[0], L.next) - y[0], r2);
-        const double dyy = neg_if_(shfl_d_(y[1], L.next) - y[1], r2);
-        const double dz = neg_if_(shfl_d_(y[2], L.next) - y[2], r2);
-        const double rr = dx * dx + dyy * dyy + dz * dz;
+        const double ex = shfl_d_(y[0], L.next) - y[0];
+        const double ey = shfl_d_(y[1], L.next) - y[1];
+        const double ez = shfl_d_(y[2], L.next) - y[2];
+        const double rr = ex * ex + ey * ey + ez * ez;
         const double r = m.sqrt_nz(rr);
         const double inv = m.div_nz(1.0, rr * r);
-        const double fa = pl[1] * inv, fb = pl[0] * inv;
-        const double d[3] = {dx, dyy, dz};
+        const double fo = pl[0] * inv, fs = pl[1] * inv;
+        const double e[3] = {ex, ey, ez};
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const double A = fa * d[c], B = fb * d[c];
-            const double recv = shfl_d_(r2 ? A : B, L.prev); /* role 2 hands A02 to role 0; roles 0, 1 hand B01, B12 on */
-            const double u = r0 ? A : neg_if_(r1 ? recv : B, true);
-            const double w = r0 ? recv : (r1 ? A : neg_if_(recv, true));
+            const double own = fo * e[c];
+            const double recv = shfl_d_(fs * e[c], L.prev);
             dy[c] = y[3 + c];
-            dy[3 + c] = (0.0 + u) + w;
+            dy[3 + c] = (0.0 + own) - recv;
         }
     }
 };
@@ -167,9 +168,17 @@ ODE_DEV void gather_full_(const Lane3& L, const double (&loc)[SS::NS], double (&
 }
 
 /* ============================================================================ Dop853, three lanes per trajectory */
-template <class SS, int OUT>
+template <class SS, int OUT, bool STAGE = false>
 struct Dop853SplitStepper {
     static constexpr int N = SS::NS, NF = SS::FULL;
+    static constexpr bool kStage = STAGE;
+    /* STAGE: recorded results leave through shared memory and the TMA engine. Every trajectory slot of
+     * the CTA owns 9 rows of NF doubles (8 coefficient rows of an interval + 1 sample row): the three lanes
+     * write their components into the rows (the layout of the result arrays), and the group's first lane
+     * hands each block to the TMA engine as ONE bulk copy (1152 B of coefficients, 144 B of state) instead
+     * of 54 scattered 8-byte stores per lane (ncu, direct stores: 16.3 GB written at 750 GB/s with
+     * long-scoreboard and LSU-queue stalls on top). */
+    static constexpr int kSlotDoubles = 9 * NF;
     static constexpr bool DENSE = OUT == ODE_B200_OUT_DENSE;
     static constexpr bool CONT8 = OUT == ODE_B200_OUT_CONTINUOUS8;
     static constexpr int kThreads = (DENSE || CONT8) ? 256 : ODE_B200_LOCK_THREADS; /* as the n = 6 lockstep kernels */
@@ -187,31 +196,94 @@ struct Dop853SplitStepper {
         long long traj;
     };
 
-    /* ---- result stores (per lane; no shuffles) */
+    /* ---- result stores (per lane; the three lanes of a group always come here together) */
+    ODE_DEV static double* slot_(const Lane3& L) {
+        return s_stage + ((threadIdx.x >> 5) * kSlotsPerWarp + L.base / 3u) * kSlotDoubles;
+    }
+    /* the slot's previous bulk copies have been read by the TMA engine (the leader issued them, so it waits),
+     * and the other two lanes learn it at the group barrier */
+    ODE_DEV static void slot_acquire_(const Lane3& L) {
+        if (L.role == 0u) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp(7u << L.base);
+    }
+    ODE_DEV static void slot_release_(const Lane3& L) { /* all three lanes have written their components */
+        __syncwarp(7u << L.base);
+        if (L.role == 0u) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    ODE_DEV static void bulk_(double* dst, const double* src_smem, int bytes) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_addr_(src_smem)),
+                     "r"(bytes)
+                     : "memory");
+    }
     ODE_DEV static void push(const KernelArgs& a, State& s, const Lane3& L, double x, const double (&y)[N]) {
         if (a.out.out_x != nullptr && (long long)s.c.out_count < a.out.out_cap) {
             const size_t q = (size_t)s.traj * (size_t)a.out_pitch + s.c.out_count;
             if (L.role == 0u) a.out.out_x[q] = x;
-            double* dst = a.out.out_y + q * NF;
+            if constexpr (STAGE) {
+                double* b = slot_(L) + 8 * NF;
+                slot_acquire_(L);
 #pragma unroll
-            for (int c = 0; c < N; ++c) dst[SS::gcomp(L.role, c)] = y[c];
+                for (int c = 0; c < N; ++c) b[SS::gcomp(L.role, c)] = y[c];
+                slot_release_(L);
+                if (L.role == 0u) {
+                    bulk_(a.out.out_y + q * NF, b, NF * 8);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            } else {
+                double* dst = a.out.out_y + q * NF;
+#pragma unroll
+                for (int c = 0; c < N; ++c) dst[SS::gcomp(L.role, c)] = y[c];
+            }
         }
         ++s.c.out_count;
     }
-    ODE_DEV static void push_com(const KernelArgs& a, State& s, const Lane3& L, double brk, double step,
-                                 const double (&rc)[8][N]) {
+    /* Continuous8: the sample (x, y) and the interval (|x|, rcont[0..7], h_old) of one accepted step */
+    ODE_DEV static void push_step(const KernelArgs& a, State& s, const Lane3& L, double x, const double (&y)[N],
+                                  double brk, double step, const double (&rc)[8][N]) {
         const ode_b200_outputs& o = a.out;
-        if (o.com_break != nullptr && (long long)s.c.com_count < o.com_cap) {
-            const size_t q = (size_t)s.traj * (size_t)a.com_pitch + s.c.com_count;
-            if (L.role == 0u) {
-                o.com_break[q] = brk;
-                o.com_step[q] = step;
+        const bool rec_y = o.out_x != nullptr && (long long)s.c.out_count < o.out_cap;
+        const bool rec_c = o.com_break != nullptr && (long long)s.c.com_count < o.com_cap;
+        const size_t qy = (size_t)s.traj * (size_t)a.out_pitch + s.c.out_count;
+        const size_t qc = (size_t)s.traj * (size_t)a.com_pitch + s.c.com_count;
+        if (L.role == 0u) {
+            if (rec_y) o.out_x[qy] = x;
+            if (rec_c) {
+                o.com_break[qc] = brk;
+                o.com_step[qc] = step;
             }
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-#pragma unroll
-                for (int c = 0; c < N; ++c) o.com_coef[(q * 8 + r) * NF + SS::gcomp(L.role, c)] = rc[r][c];
         }
+        if constexpr (STAGE) {
+            if (rec_y || rec_c) {
+                double* b = slot_(L);
+                slot_acquire_(L);
+#pragma unroll
+                for (int c = 0; c < N; ++c) b[8 * NF + SS::gcomp(L.role, c)] = y[c];
+                if (rec_c) {
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+#pragma unroll
+                        for (int c = 0; c < N; ++c) b[r * NF + SS::gcomp(L.role, c)] = rc[r][c];
+                }
+                slot_release_(L);
+                if (L.role == 0u) {
+                    if (rec_c) bulk_(o.com_coef + qc * (8 * NF), b, 8 * NF * 8);
+                    if (rec_y) bulk_(o.out_y + qy * NF, b + 8 * NF, NF * 8);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+        } else {
+            if (rec_y) {
+#pragma unroll
+                for (int c = 0; c < N; ++c) o.out_y[qy * NF + SS::gcomp(L.role, c)] = y[c];
+            }
+            if (rec_c) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+#pragma unroll
+                    for (int c = 0; c < N; ++c) o.com_coef[(qc * 8 + r) * NF + SS::gcomp(L.role, c)] = rc[r][c];
+            }
+        }
+        s.c.out_count += 1;
         s.c.com_count += 1;
     }
     ODE_DEV static void finish(State& s, const KernelArgs& a, const Lane3& L, int status) {
@@ -234,6 +306,8 @@ struct Dop853SplitStepper {
             if (o.out_count) o.out_count[t] = s.c.out_count;
             if (o.com_count) o.com_count[t] = s.c.com_count;
             if (o.com_lower) o.com_lower[t] = CONT8 ? a.cfg.x0 : 0.0;
+            /* the slot goes to the next trajectory only after the TMA engine has read it */
+            if constexpr (STAGE) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
     }
 
@@ -704,8 +778,7 @@ struct Dop853SplitStepper {
                     }
                 }
             } else if constexpr (CONT8) {
-                push(a, s, L, s.x, s.y);
-                push_com(a, s, L, fabs(s.x), s.h_old, rc);
+                push_step(a, s, L, s.x, s.y, fabs(s.x), s.h_old, rc);
             } else {
                 push(a, s, L, cfg.x0, s.y); /* pushes x0, not x (Q6) */
             }
