@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define ODE_B200_ABI_VERSION 1
+#define ODE_B200_ABI_VERSION 2
 #define ODE_B200_MAX_DIM 32
 #define ODE_B200_MAX_PARAMS 16
 
@@ -237,24 +237,61 @@ int ode_b200_integrate_batch_multi(int sys_id, const ode_b200_config* cfg, int64
                                    int n_gpus, const ode_b200_outputs* out);
 
 /*
- * f32 instantiation of the fixed-step path (`impl FloatNumber for f32`, src/dop_shared.rs:74;
- * examples/bouncing_ball.rs:15,36 runs Rk4 in f32): Rk4::new(f, x, y, x_end, step_size) and
- * Rk4::integrate with T = f32, every operation in single precision. Available for the built-in
- * systems whose RHS needs no libm call (lorenz, robertson, bouncing_ball, test_rk4_1, test_rk4_2).
- * Host pointers; layouts as in ode_b200_outputs. The adaptive methods stay f64-only (their f32
- * form needs a second libm clone, powf).
+ * ---- T = f32 ---------------------------------------------------------------------
+ * The crate is generic over FloatNumber = {f32, f64} (src/dop_shared.rs:52-77); examples/bouncing_ball.rs
+ * runs Rk4 in f32 (:15,36) and names Dopri5 in f32 as the alternative (:35). These entry points are the
+ * three steppers with T = f32: every operation in single precision, every literal and tableau
+ * coefficient the f64 value rounded to f32 (T::from / to_subset), powf the host libm's. Available for the
+ * built-in systems whose right-hand side needs no libm call (lorenz, robertson, bouncing_ball,
+ * test_rk4_1, test_rk4_2). Host pointers; layouts as for f64. A coverage path, not the hot one: the
+ * kernels are generic loops over the state (one trajectory per thread), not the tuned f64 kernels.
  */
-typedef struct ode_b200_outputs_f32 {
-    float*    y_final;   /* [d][n] */
-    float*    x_final;   /* [n] */
-    uint32_t* num_eval;  /* [n] */
-    uint32_t* accepted;  /* [n] */
-    int32_t*  status;    /* [n] */
+typedef struct ode_b200_config_f32 { /* ode_b200_config with T = f32, field for field */
+    int32_t method;
+    int32_t out_type;
+    float x0, x_end, dx;
+    float rtol, atol;
+    float safety_factor, alpha, beta, fac_min, fac_max, h_max, h0;
+    float uround;    /* Dopri5::new: f32::EPSILON (dopri5.rs:89); from_param and Dop853: f64::EPSILON as f32 (Q3) */
+    float step_size;
+    uint32_t n_max, n_stiff;
+} ode_b200_config_f32;
+
+typedef struct ode_b200_outputs_f32 { /* ode_b200_outputs with T = f32, field for field */
+    float*    y_final;
+    float*    x_final;
+    float*    h_next;
+    uint32_t* num_eval;
+    uint32_t* accepted;
+    uint32_t* rejected;
+    uint32_t* n_step;
+    int32_t*  status;
     int64_t   out_cap;
-    float*    out_x;     /* [n][out_cap] */
-    float*    out_y;     /* [n][out_cap][d] */
-    uint32_t* out_count; /* [n] */
+    float*    out_x;
+    float*    out_y;
+    uint32_t* out_count;
+    int64_t   com_cap;
+    float*    com_lower;
+    float*    com_break;
+    float*    com_step;
+    float*    com_coef;
+    uint32_t* com_count;
 } ode_b200_outputs_f32;
+
+/* Dopri5::<f32>::new / Dop853::<f32>::new, ::from_param, Rk4::<f32>::new */
+int ode_b200_config_new_f32(int method, float x, float x_end, float dx, float rtol, float atol,
+                            ode_b200_config_f32* out);
+int ode_b200_config_from_param_f32(int method, float x, float x_end, float dx, float rtol, float atol,
+                                   float safety_factor, float beta, float fac_min, float fac_max,
+                                   float h_max, float h, uint32_t n_max, uint32_t n_stiff, int out_type,
+                                   ode_b200_config_f32* out);
+int ode_b200_config_rk4_f32(float x, float x_end, float step_size, ode_b200_config_f32* out);
+/* integrate() / integrate_with_continuous_output_model() with T = f32 for a batch (all three methods;
+ * ODE_B200_OUT_CONTINUOUS8 is not available in f32) */
+int ode_b200_integrate_batch_f32(ode_b200_ctx* ctx, int sys_id, const ode_b200_config_f32* cfg,
+                                 int64_t n_traj, const float* y0, const float* params,
+                                 int params_per_traj, const ode_b200_outputs_f32* out);
+/* Rk4::<f32>::new(f, x, y, x_end, step_size) + integrate(): ode_b200_config_rk4_f32 + the call above */
 int ode_b200_rk4_f32_integrate_batch(ode_b200_ctx* ctx, int sys_id, float x, float x_end, float step_size,
                                      int64_t n_traj, const float* y0, const float* params,
                                      int params_per_traj, const ode_b200_outputs_f32* out);

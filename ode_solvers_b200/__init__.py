@@ -9,4 +9,5 @@ from .api import (Context, ContinuousOutputModel, Dop853, Dopri5, DynSystem, Int
                   MaxNumStepReached, Ode200Error, OutputType, Rk4, SolverResult, Stats,
                   StepSizeUnderflow, StiffnessDetected, System, UnsupportedDomain, com_evaluate_batch,
                   config_from_param, config_new, config_rk4, default_context, device_count,
-                  integrate_batch, measure_fp64_peak, rk4_f32_integrate_batch, save)
+                  integrate_batch, integrate_batch_f32, config_new_f32, config_from_param_f32, config_rk4_f32,
+                  measure_fp64_peak, rk4_f32_integrate_batch, save)

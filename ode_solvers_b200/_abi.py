@@ -58,40 +58,62 @@ class Outputs(C.Structure):
 c_float_p = C.POINTER(C.c_float)
 
 
-class OutputsF32(C.Structure):
-    """ode_b200_outputs_f32."""
+class ConfigF32(C.Structure):
+    """ode_b200_config_f32: ode_b200_config with T = f32, field for field."""
     _fields_ = [
-        ("y_final", c_float_p), ("x_final", c_float_p), ("num_eval", c_u32_p), ("accepted", c_u32_p),
-        ("status", c_i32_p), ("out_cap", C.c_int64), ("out_x", c_float_p), ("out_y", c_float_p),
-        ("out_count", c_u32_p),
+        ("method", C.c_int32), ("out_type", C.c_int32),
+        ("x0", C.c_float), ("x_end", C.c_float), ("dx", C.c_float),
+        ("rtol", C.c_float), ("atol", C.c_float),
+        ("safety_factor", C.c_float), ("alpha", C.c_float), ("beta", C.c_float),
+        ("fac_min", C.c_float), ("fac_max", C.c_float), ("h_max", C.c_float),
+        ("h0", C.c_float), ("uround", C.c_float), ("step_size", C.c_float),
+        ("n_max", C.c_uint32), ("n_stiff", C.c_uint32),
+    ]
+
+
+class OutputsF32(C.Structure):
+    """ode_b200_outputs_f32: ode_b200_outputs with T = f32, field for field."""
+    _fields_ = [
+        ("y_final", c_float_p), ("x_final", c_float_p), ("h_next", c_float_p),
+        ("num_eval", c_u32_p), ("accepted", c_u32_p), ("rejected", c_u32_p), ("n_step", c_u32_p),
+        ("status", c_i32_p),
+        ("out_cap", C.c_int64), ("out_x", c_float_p), ("out_y", c_float_p), ("out_count", c_u32_p),
+        ("com_cap", C.c_int64), ("com_lower", c_float_p), ("com_break", c_float_p),
+        ("com_step", c_float_p), ("com_coef", c_float_p), ("com_count", c_u32_p),
     ]
 
 
 class HostOutputsF32:
     """numpy-backed ode_b200_outputs_f32."""
 
-    def __init__(self, n, dim, out_cap=0):
-        self.n, self.dim, self.out_cap = n, dim, int(out_cap)
+    def __init__(self, n, dim, out_cap=0, com_cap=0, m=5):
+        self.n, self.dim, self.out_cap, self.com_cap, self.m = n, dim, int(out_cap), int(com_cap), m
         self.y_final = np.zeros((dim, n), dtype=np.float32)
         self.x_final = np.zeros(n, dtype=np.float32)
+        self.h_next = np.zeros(n, dtype=np.float32)
         self.num_eval = np.zeros(n, dtype=np.uint32)
         self.accepted = np.zeros(n, dtype=np.uint32)
+        self.rejected = np.zeros(n, dtype=np.uint32)
+        self.n_step = np.zeros(n, dtype=np.uint32)
         self.status = np.full(n, -1, dtype=np.int32)
         self.out_count = np.zeros(n, dtype=np.uint32)
         self.out_x = np.zeros((n, out_cap), dtype=np.float32) if out_cap else None
         self.out_y = np.zeros((n, out_cap, dim), dtype=np.float32) if out_cap else None
+        self.com_lower = np.zeros(n, dtype=np.float32)
+        self.com_count = np.zeros(n, dtype=np.uint32)
+        self.com_break = np.zeros((n, com_cap), dtype=np.float32) if com_cap else None
+        self.com_step = np.zeros((n, com_cap), dtype=np.float32) if com_cap else None
+        self.com_coef = np.zeros((n, com_cap, m, dim), dtype=np.float32) if com_cap else None
 
     def struct(self):
         o = OutputsF32()
-        o.y_final = _ptr(self.y_final, c_float_p)
-        o.x_final = _ptr(self.x_final, c_float_p)
-        o.num_eval = _ptr(self.num_eval, c_u32_p)
-        o.accepted = _ptr(self.accepted, c_u32_p)
+        for k in ("y_final", "x_final", "h_next", "out_x", "out_y", "com_lower", "com_break", "com_step", "com_coef"):
+            setattr(o, k, _ptr(getattr(self, k), c_float_p))
+        for k in ("num_eval", "accepted", "rejected", "n_step", "out_count", "com_count"):
+            setattr(o, k, _ptr(getattr(self, k), c_u32_p))
         o.status = _ptr(self.status, c_i32_p)
         o.out_cap = self.out_cap
-        o.out_x = _ptr(self.out_x, c_float_p)
-        o.out_y = _ptr(self.out_y, c_float_p)
-        o.out_count = _ptr(self.out_count, c_u32_p)
+        o.com_cap = self.com_cap
         return o
 
 
@@ -159,7 +181,8 @@ ABI_SYMBOLS = [
     "ode_b200_set_zero_copy", "ode_b200_set_lane_split",
     "ode_b200_stream",
     "ode_b200_integrate_batch", "ode_b200_integrate_batch_device", "ode_b200_integrate_batch_multi",
-    "ode_b200_rk4_f32_integrate_batch",
+    "ode_b200_rk4_f32_integrate_batch", "ode_b200_integrate_batch_f32",
+    "ode_b200_config_new_f32", "ode_b200_config_from_param_f32", "ode_b200_config_rk4_f32",
     "ode_b200_set_work_queue", "ode_b200_com_evaluate",
     "ode_b200_tableau", "ode_b200_debug_pow", "ode_b200_debug_exp", "ode_b200_debug_div", "ode_b200_debug_powf",
 ]
@@ -178,6 +201,19 @@ def declare_config_fns(lib, prefix):
     f.restype = C.c_int
     f = getattr(lib, prefix + "config_rk4")
     f.argtypes = [C.c_double] * 3 + [C.POINTER(Config)]
+    f.restype = C.c_int
+
+
+def declare_config_fns_f32(lib, prefix):
+    """the f32 constructors (shared by product and oracle)"""
+    f = getattr(lib, prefix + "config_new_f32")
+    f.argtypes = [C.c_int] + [C.c_float] * 5 + [C.POINTER(ConfigF32)]
+    f.restype = C.c_int
+    f = getattr(lib, prefix + "config_from_param_f32")
+    f.argtypes = [C.c_int] + [C.c_float] * 11 + [C.c_uint32, C.c_uint32, C.c_int] + [C.POINTER(ConfigF32)]
+    f.restype = C.c_int
+    f = getattr(lib, prefix + "config_rk4_f32")
+    f.argtypes = [C.c_float] * 3 + [C.POINTER(ConfigF32)]
     f.restype = C.c_int
 
 
@@ -230,6 +266,10 @@ def load():
     lib.ode_b200_rk4_f32_integrate_batch.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int64,
                                                      C.c_void_p, C.c_void_p, C.c_int, C.POINTER(OutputsF32)]
     lib.ode_b200_rk4_f32_integrate_batch.restype = C.c_int
+    declare_config_fns_f32(lib, "ode_b200_")
+    lib.ode_b200_integrate_batch_f32.argtypes = [C.c_void_p, C.c_int, C.POINTER(ConfigF32), C.c_int64, C.c_void_p,
+                                                 C.c_void_p, C.c_int, C.POINTER(OutputsF32)]
+    lib.ode_b200_integrate_batch_f32.restype = C.c_int
     lib.ode_b200_set_work_queue.argtypes = [C.c_void_p, C.c_int]
     lib.ode_b200_set_work_queue.restype = C.c_int
     lib.ode_b200_set_zero_copy.argtypes = [C.c_void_p, C.c_int]

@@ -314,9 +314,56 @@ def integrate_batch(system, cfg, y0, params=None, out_cap=0, com_cap=0, ctx=None
     return out
 
 
+def config_new_f32(method, x, x_end, dx, rtol, atol, out_type=None):
+    """Dopri5::<f32>::new / Dop853::<f32>::new (dopri5.rs:76, dop853.rs:76 with T = f32)"""
+    c = _abi.ConfigF32()
+    _check(_abi.load().ode_b200_config_new_f32(method, x, x_end, dx, rtol, atol, C.byref(c)), "config_new_f32")
+    if out_type is not None:
+        c.out_type = out_type
+    return c
+
+
+def config_from_param_f32(method, x, x_end, dx, rtol, atol, safety_factor, beta, fac_min, fac_max, h_max, h, n_max,
+                          n_stiff, out_type):
+    c = _abi.ConfigF32()
+    _check(_abi.load().ode_b200_config_from_param_f32(method, x, x_end, dx, rtol, atol, safety_factor, beta, fac_min,
+                                                      fac_max, h_max, h, n_max, n_stiff, int(out_type), C.byref(c)),
+           "config_from_param_f32")
+    return c
+
+
+def config_rk4_f32(x, x_end, step_size):
+    c = _abi.ConfigF32()
+    _check(_abi.load().ode_b200_config_rk4_f32(x, x_end, step_size, C.byref(c)), "config_rk4_f32")
+    return c
+
+
+def integrate_batch_f32(system, cfg, y0, params=None, out_cap=0, com_cap=0, ctx=None):
+    """The three steppers with T = f32 (`impl FloatNumber for f32`, src/dop_shared.rs:74) for a batch.
+    cfg: _abi.ConfigF32; y0: [dim, n] float32. Returns an _abi.HostOutputsF32."""
+    lib = _abi.load()
+    ctx = ctx or default_context(0)
+    y0 = np.ascontiguousarray(np.asarray(y0, dtype=np.float32).reshape(system.dim, -1))
+    n = y0.shape[1]
+    if params is None:
+        params = system.params
+    per_traj, pp = 0, None
+    if system.n_params:
+        if params is None:
+            raise ValueError("system %s needs %d parameters" % (system.name, system.n_params))
+        params = np.ascontiguousarray(np.asarray(params, dtype=np.float32))
+        per_traj = int(params.ndim == 2)
+        pp = params.ctypes.data
+    out = _abi.HostOutputsF32(n, system.dim, out_cap, com_cap, 5)
+    s = out.struct()
+    _check(lib.ode_b200_integrate_batch_f32(ctx.handle, system.sys_id, C.byref(cfg), n, y0.ctypes.data, pp, per_traj,
+                                            C.byref(s)), "integrate_batch_f32")
+    out.kernel_ms = ctx.last_kernel_ms
+    return out
+
+
 def rk4_f32_integrate_batch(system, x, x_end, step_size, y0, params=None, out_cap=0, ctx=None):
-    """Rk4 with T = f32 (src/rk4.rs over FloatNumber for f32, src/dop_shared.rs:74) for a batch.
-    y0: [dim, n] float32. Returns an _abi.HostOutputsF32."""
+    """Rk4::<f32>::new(f, x, y, x_end, step_size) + integrate() for a batch (the ABI's convenience entry)."""
     lib = _abi.load()
     ctx = ctx or default_context(0)
     y0 = np.ascontiguousarray(np.asarray(y0, dtype=np.float32).reshape(system.dim, -1))

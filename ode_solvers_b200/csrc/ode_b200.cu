@@ -679,14 +679,103 @@ extern "C" int ode_b200_integrate_batch(ode_b200_ctx* c, int sys_id, const ode_b
 }
 
 /* Rk4 with T = f32 (see include/ode_b200.h) */
-static int rk4_f32_impl(ode_b200_ctx* c, int sys_id, float x, float x_end, float step_size, int64_t n,
-                        const float* y0, const float* params, int per_traj, const ode_b200_outputs_f32* out);
+/* ---- T = f32: constructors (every literal through T::from, every operation in f32) ------------------ */
+static const float kEpsF64AsF32 = (float)2.220446049250313e-16; /* T::from(f64::EPSILON) */
 
-extern "C" int ode_b200_rk4_f32_integrate_batch(ode_b200_ctx* c, int sys_id, float x, float x_end, float step_size,
-                                                int64_t n, const float* y0, const float* params, int per_traj,
-                                                const ode_b200_outputs_f32* out) {
+/* Dopri5::<f32>::new (dopri5.rs:14-27,76-105: uround = T::epsilon(), Q3); Dop853::<f32>::new (dop853.rs:14-27,76-109) */
+extern "C" int ode_b200_config_new_f32(int method, float x, float x_end, float dx, float rtol, float atol,
+                                       ode_b200_config_f32* c) {
+    if (!c) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "config is NULL");
+    memset(c, 0, sizeof(*c));
+    c->method = method;
+    c->out_type = ODE_B200_OUT_DENSE;
+    c->x0 = x;
+    c->x_end = x_end;
+    c->dx = dx;
+    c->rtol = rtol;
+    c->atol = atol;
+    c->safety_factor = (float)0.9;
+    c->h_max = x_end - x;
+    c->h0 = 0.0f;
+    c->n_max = 100000;
+    c->n_stiff = 1000;
+    if (method == ODE_B200_DOPRI5) {
+        c->alpha = (float)(0.2 - 0.04 * 0.75); /* T::from(0.2 - 0.04 * 0.75): the f64 value, then rounded */
+        c->beta = (float)0.04;
+        c->fac_max = (float)10.0;
+        c->fac_min = (float)0.2;
+        c->uround = 1.1920929e-07f; /* f32::EPSILON = 2^-23 */
+    } else if (method == ODE_B200_DOP853) {
+        c->alpha = 1.0f / (float)8.0;
+        c->beta = 0.0f;
+        c->fac_max = (float)6.0;
+        c->fac_min = (float)0.333;
+        c->uround = kEpsF64AsF32;
+    } else {
+        return fail(ODE_B200_ERR_INVALID_ARGUMENT, "config_new_f32: method must be DOPRI5 or DOP853");
+    }
+    return ODE_B200_SUCCESS;
+}
+
+/* Dopri5::<f32>::from_param (dopri5.rs:129-184); Dop853::<f32>::from_param (dop853.rs:133-192) */
+extern "C" int ode_b200_config_from_param_f32(int method, float x, float x_end, float dx, float rtol, float atol,
+                                              float safety_factor, float beta, float fac_min, float fac_max,
+                                              float h_max, float h, uint32_t n_max, uint32_t n_stiff, int out_type,
+                                              ode_b200_config_f32* c) {
+    if (!c) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "config is NULL");
+    if (out_type < ODE_B200_OUT_DENSE || out_type > ODE_B200_OUT_CONTINUOUS)
+        return fail(ODE_B200_ERR_INVALID_ARGUMENT, "config_from_param_f32: bad out_type");
+    memset(c, 0, sizeof(*c));
+    c->method = method;
+    c->out_type = out_type;
+    c->x0 = x;
+    c->x_end = x_end;
+    c->dx = dx;
+    c->rtol = rtol;
+    c->atol = atol;
+    c->safety_factor = safety_factor;
+    c->beta = beta;
+    c->fac_min = fac_min;
+    c->fac_max = fac_max;
+    c->h_max = h_max;
+    c->h0 = h;
+    c->uround = kEpsF64AsF32;
+    c->n_max = n_max;
+    c->n_stiff = n_stiff;
+    volatile float b = beta; /* two roundings: the product, then the difference */
+    if (method == ODE_B200_DOPRI5) {
+        volatile float t = b * (float)0.75;
+        c->alpha = (float)0.2 - t;
+    } else if (method == ODE_B200_DOP853) {
+        volatile float t = b * (float)0.2;
+        c->alpha = 1.0f / (float)8.0 - t;
+    } else {
+        return fail(ODE_B200_ERR_INVALID_ARGUMENT, "config_from_param_f32: method must be DOPRI5 or DOP853");
+    }
+    return ODE_B200_SUCCESS;
+}
+
+/* Rk4::<f32>::new (rk4.rs:42-68) */
+extern "C" int ode_b200_config_rk4_f32(float x, float x_end, float step_size, ode_b200_config_f32* c) {
+    if (!c) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "config is NULL");
+    memset(c, 0, sizeof(*c));
+    c->method = ODE_B200_RK4;
+    c->out_type = ODE_B200_OUT_SPARSE;
+    c->x0 = x;
+    c->x_end = x_end;
+    c->step_size = step_size;
+    return ODE_B200_SUCCESS;
+}
+
+/* ---- T = f32: the batched entry (see include/ode_b200.h) ------------------------------------------- */
+static int integrate_f32_impl(ode_b200_ctx* c, int sys_id, const ode_b200_config_f32* cfg, int64_t n, const float* y0,
+                              const float* params, int per_traj, const ode_b200_outputs_f32* out);
+
+extern "C" int ode_b200_integrate_batch_f32(ode_b200_ctx* c, int sys_id, const ode_b200_config_f32* cfg, int64_t n,
+                                            const float* y0, const float* params, int per_traj,
+                                            const ode_b200_outputs_f32* out) {
     if (!c) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
-    const int rc = rk4_f32_impl(c, sys_id, x, x_end, step_size, n, y0, params, per_traj, out);
+    const int rc = integrate_f32_impl(c, sys_id, cfg, n, y0, params, per_traj, out);
     if (rc != ODE_B200_SUCCESS && c->stream) { /* see integrate_range */
         const std::string keep = g_last_error;
         cudaStreamSynchronize(c->stream);
@@ -696,15 +785,28 @@ extern "C" int ode_b200_rk4_f32_integrate_batch(ode_b200_ctx* c, int sys_id, flo
     return rc;
 }
 
-static int rk4_f32_impl(ode_b200_ctx* c, int sys_id, float x, float x_end, float step_size, int64_t n,
-                        const float* y0, const float* params, int per_traj, const ode_b200_outputs_f32* out) {
+extern "C" int ode_b200_rk4_f32_integrate_batch(ode_b200_ctx* c, int sys_id, float x, float x_end, float step_size,
+                                                int64_t n, const float* y0, const float* params, int per_traj,
+                                                const ode_b200_outputs_f32* out) {
+    ode_b200_config_f32 cfg;
+    ode_b200_config_rk4_f32(x, x_end, step_size, &cfg);
+    return ode_b200_integrate_batch_f32(c, sys_id, &cfg, n, y0, params, per_traj, out);
+}
+
+static int integrate_f32_impl(ode_b200_ctx* c, int sys_id, const ode_b200_config_f32* cfg, int64_t n, const float* y0,
+                              const float* params, int per_traj, const ode_b200_outputs_f32* out) {
     if (sys_id < 0 || sys_id >= kNumBuiltins) return fail(ODE_B200_ERR_UNKNOWN_SYSTEM, "f32 needs a built-in system");
+    if (!cfg || !out) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "f32: cfg / out is NULL");
+    if (cfg->method < ODE_B200_RK4 || cfg->method > ODE_B200_DOP853) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "bad method");
+    if (cfg->out_type < ODE_B200_OUT_DENSE || cfg->out_type > ODE_B200_OUT_CONTINUOUS)
+        return fail(ODE_B200_ERR_INVALID_ARGUMENT, "f32: out_type must be Dense, Sparse or Continuous");
     const SystemEntry* e = kBuiltins[sys_id];
-    if (!e->rk4_f32_kernel)
-        return fail(ODE_B200_ERR_UNKNOWN_SYSTEM, std::string("system '") + e->name + "' has no f32 instantiation");
-    if (!out || n < 0 || (n > 0 && !y0) || (n > 0 && e->n_params > 0 && !params) || out->out_cap < 0 ||
-        (out->out_cap > 0 && (!out->out_x || !out->out_y)))
-        return fail(ODE_B200_ERR_INVALID_ARGUMENT, "rk4_f32: bad arguments");
+    const void* fn = e->f32_kernels[cfg->method];
+    if (!fn) return fail(ODE_B200_ERR_UNKNOWN_SYSTEM, std::string("system '") + e->name + "' has no f32 instantiation");
+    if (n < 0 || (n > 0 && !y0) || (n > 0 && e->n_params > 0 && !params) || out->out_cap < 0 || out->com_cap < 0 ||
+        (out->out_cap > 0 && (!out->out_x || !out->out_y)) ||
+        (out->com_cap > 0 && (!out->com_break || !out->com_step || !out->com_coef)))
+        return fail(ODE_B200_ERR_INVALID_ARGUMENT, "integrate_batch_f32: bad arguments");
     if (n == 0) return ODE_B200_SUCCESS;
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
@@ -718,9 +820,7 @@ static int rk4_f32_impl(ode_b200_ctx* c, int sys_id, float x, float x_end, float
     }
     KernelArgsF32 ka;
     memset(&ka, 0, sizeof(ka));
-    ka.x0 = x;
-    ka.x_end = x_end;
-    ka.step_size = step_size;
+    ka.cfg = *cfg;
     ka.n_traj = n;
     ka.y0 = (const float*)c->y0.p;
     ka.params = (const float*)c->params.p;
@@ -728,6 +828,7 @@ static int rk4_f32_impl(ode_b200_ctx* c, int sys_id, float x, float x_end, float
     ka.use_queue = c->use_queue;
     ka.queue = c->queue + (c->launches % kQueueSlots);
     ode_b200_outputs_f32& dv = ka.out;
+    const size_t cap = (size_t)out->out_cap, ccap = (size_t)out->com_cap;
 #define WANT32(field, buf, bytes)                                 \
     if (out->field) {                                             \
         if (ensure(c, c->buf, (bytes))) return ODE_B200_ERR_CUDA; \
@@ -735,26 +836,37 @@ static int rk4_f32_impl(ode_b200_ctx* c, int sys_id, float x, float x_end, float
     }
     WANT32(y_final, y_final, d * n * 4)
     WANT32(x_final, x_final, n * 4)
+    WANT32(h_next, h_next, n * 4)
     WANT32(num_eval, num_eval, n * 4)
     WANT32(accepted, accepted, n * 4)
+    WANT32(rejected, rejected, n * 4)
+    WANT32(n_step, n_step, n * 4)
     WANT32(status, status, n * 4)
     WANT32(out_count, out_count, n * 4)
-    if (out->out_cap > 0) {
+    WANT32(com_count, com_count, n * 4)
+    WANT32(com_lower, com_lower, n * 4)
+    if (cap > 0) {
         dv.out_cap = out->out_cap;
-        WANT32(out_x, out_x, (size_t)n * out->out_cap * 4)
-        WANT32(out_y, out_y, (size_t)n * out->out_cap * d * 4)
+        WANT32(out_x, out_x, (size_t)n * cap * 4)
+        WANT32(out_y, out_y, (size_t)n * cap * d * 4)
+    }
+    if (ccap > 0) {
+        dv.com_cap = out->com_cap;
+        WANT32(com_break, com_break, (size_t)n * ccap * 4)
+        WANT32(com_step, com_step, (size_t)n * ccap * 4)
+        WANT32(com_coef, com_coef, (size_t)n * ccap * 5 * d * 4)
     }
 #undef WANT32
-    const int block = 128; /* __launch_bounds__ of ode_rk4_f32_kernel */
+    const int block = 128; /* __launch_bounds__ of ode_f32_step_loop_kernel */
     const long long blocks_all = (n + block - 1) / block;
     int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, e->rk4_f32_kernel, block, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block, 0));
     long long grid = blocks_all;
     if (c->use_queue) grid = std::min<long long>(blocks_all, (long long)c->num_sms * std::max(per_sm, 1));
     CUDA_TRY(cudaMemsetAsync(ka.queue, 0, sizeof(unsigned long long), st));
     CUDA_TRY(cudaEventRecord(c->ev0, st));
     void* args[] = {&ka};
-    CUDA_TRY(cudaLaunchKernel(e->rk4_f32_kernel, dim3((unsigned)grid), dim3(block), args, 0, st));
+    CUDA_TRY(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(block), args, 0, st));
     CUDA_TRY(cudaEventRecord(c->ev1, st));
     c->timed = true;
     c->launches++;
@@ -762,13 +874,23 @@ static int rk4_f32_impl(ode_b200_ctx* c, int sys_id, float x, float x_end, float
     if (out->field) CUDA_TRY(cudaMemcpyAsync(out->field, dv.field, (bytes), cudaMemcpyDeviceToHost, st));
     BACK32(y_final, d * n * 4)
     BACK32(x_final, n * 4)
+    BACK32(h_next, n * 4)
     BACK32(num_eval, n * 4)
     BACK32(accepted, n * 4)
+    BACK32(rejected, n * 4)
+    BACK32(n_step, n * 4)
     BACK32(status, n * 4)
     BACK32(out_count, n * 4)
-    if (out->out_cap > 0) {
-        BACK32(out_x, (size_t)n * out->out_cap * 4)
-        BACK32(out_y, (size_t)n * out->out_cap * d * 4)
+    BACK32(com_count, n * 4)
+    BACK32(com_lower, n * 4)
+    if (cap > 0) {
+        BACK32(out_x, (size_t)n * cap * 4)
+        BACK32(out_y, (size_t)n * cap * d * 4)
+    }
+    if (ccap > 0) {
+        BACK32(com_break, (size_t)n * ccap * 4)
+        BACK32(com_step, (size_t)n * ccap * 4)
+        BACK32(com_coef, (size_t)n * ccap * 5 * d * 4)
     }
 #undef BACK32
     CUDA_TRY(cudaStreamSynchronize(st));

@@ -10,15 +10,20 @@
 #include "ode_registry.h"
 #include "ode_systems.cuh"
 
+#include "ode_f32.cuh"
+
 namespace ode_b200 {
-template <class Sys>
-const void* rk4_f32_kernel_ptr() {
+template <class Sys, int METHOD>
+const void* f32_kernel_ptr() {
     if constexpr (Sys::HAS_F32)
-        return (const void*)&ode_rk4_f32_kernel<Sys>;
+        return (const void*)&ode_f32_step_loop_kernel<Sys, METHOD>;
     else
         return nullptr;
 }
 }  // namespace ode_b200
+#define ODE_B200_F32_KSET(SYS)                                                                                \
+    {ode_b200::f32_kernel_ptr<ode_b200::SYS, ODE_B200_RK4>(), ode_b200::f32_kernel_ptr<ode_b200::SYS, ODE_B200_DOPRI5>(), \
+     ode_b200::f32_kernel_ptr<ode_b200::SYS, ODE_B200_DOP853>()}
 
 #define ODE_B200_KPTR(...) ((const void*)&ode_b200::ode_step_loop_kernel<__VA_ARGS__>)
 
@@ -36,7 +41,7 @@ const void* rk4_f32_kernel_ptr() {
 #define ODE_B200_DEFINE_SYSTEM(SYS, NAME)                                                \
     extern "C" const ode_b200::SystemEntry ode_b200_entry_##NAME = {                     \
         #NAME, ode_b200::SYS::DIM, ode_b200::SYS::NP, ode_b200::SYS::HAS_SOLOUT ? 1 : 0, \
-        {ODE_B200_KSET(SYS, false), ODE_B200_KSET(SYS, true)}, ode_b200::rk4_f32_kernel_ptr<ode_b200::SYS>(), \
+        {ODE_B200_KSET(SYS, false), ODE_B200_KSET(SYS, true)}, ODE_B200_F32_KSET(SYS), \
         {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}}, {0, 0, 0, 0}, 0, 0};
 
 /* a system that also has a three-lanes-per-trajectory form (ode_split.cuh) for Dop853 */
@@ -49,7 +54,7 @@ const void* rk4_f32_kernel_ptr() {
 #define ODE_B200_DEFINE_SYSTEM_WITH_SPLIT(SYS, NAME, SPLIT)                                                   \
     extern "C" const ode_b200::SystemEntry ode_b200_entry_##NAME = {                                          \
         #NAME, ode_b200::SYS::DIM, ode_b200::SYS::NP, ode_b200::SYS::HAS_SOLOUT ? 1 : 0,                      \
-        {ODE_B200_KSET(SYS, false), ODE_B200_KSET(SYS, true)}, ode_b200::rk4_f32_kernel_ptr<ode_b200::SYS>(), \
+        {ODE_B200_KSET(SYS, false), ODE_B200_KSET(SYS, true)}, ODE_B200_F32_KSET(SYS), \
         {ODE_B200_SPLIT_KSET(SPLIT, false), ODE_B200_SPLIT_KSET(SPLIT, true)},                                \
         {ODE_B200_SPLIT_THREADS(SPLIT, ODE_B200_OUT_DENSE), ODE_B200_SPLIT_THREADS(SPLIT, ODE_B200_OUT_SPARSE), \
          ODE_B200_SPLIT_THREADS(SPLIT, ODE_B200_OUT_SPARSE), ODE_B200_SPLIT_THREADS(SPLIT, ODE_B200_OUT_CONTINUOUS8)}, \

@@ -94,9 +94,9 @@ struct KernelArgs {
                                    the host-buffer entry pads its rows to a multiple of 4) */
 };
 
-/* the f32 Rk4 kernel's arguments (device pointers) */
+/* the f32 kernels' arguments (device pointers) */
 struct KernelArgsF32 {
-    float x0, x_end, step_size;
+    ode_b200_config_f32 cfg;
     long long n_traj;
     const float* y0;
     const float* params;

@@ -908,117 +908,6 @@ struct Dop853Stepper {
     }
 };
 
-/* ============================================================================ Rk4, f32 */
-/* Rk4<f32, ...> (src/rk4.rs with T = f32, the type examples/bouncing_ball.rs:15 uses): the same
- * statements as Rk4Stepper with every operation in single precision (-fmad=false keeps FMUL and
- * FADD apart, division is IEEE). No staging: this path is a coverage row, not the hot one. */
-template <class Sys>
-struct Rk4StepperF32 {
-    static constexpr int N = Sys::DIM;
-    static constexpr bool kStage = false;
-    static constexpr bool kLockstep = false;
-    static constexpr int kRefillIdle = 1;
-    static constexpr int kThreads = 128;
-    static constexpr int kMinBlocks = 5;
-    struct State {
-        float y[N];
-        float p[Sys::NP > 0 ? Sys::NP : 1];
-        float x;
-        unsigned long long steps_left;
-        unsigned num_eval, accepted, out_count;
-        long long traj;
-        int status;
-        Counters c; /* unused; keeps run_lanes_ generic */
-    };
-
-    ODE_DEV static void push(const KernelArgsF32& a, State& s, float x, const float (&y)[N]) {
-        if (a.out.out_x != nullptr && (long long)s.out_count < a.out.out_cap) {
-            const size_t q = (size_t)s.traj * (size_t)a.out.out_cap + s.out_count;
-            a.out.out_x[q] = x;
-#pragma unroll
-            for (int i = 0; i < N; ++i) a.out.out_y[q * N + i] = y[i];
-        }
-        ++s.out_count;
-    }
-
-    ODE_DEV static bool finish(const KernelArgsF32& a, State& s) {
-        const ode_b200_outputs_f32& o = a.out;
-        int status = s.status;
-        if (status == ODE_B200_OK && o.out_cap > 0 && (long long)s.out_count > o.out_cap)
-            status = ODE_B200_OUTPUT_CAPACITY_EXCEEDED;
-        if (o.y_final)
-#pragma unroll
-            for (int i = 0; i < N; ++i) o.y_final[(size_t)i * a.n_traj + s.traj] = s.y[i];
-        if (o.x_final) o.x_final[s.traj] = s.x;
-        if (o.num_eval) o.num_eval[s.traj] = s.num_eval;
-        if (o.accepted) o.accepted[s.traj] = s.accepted;
-        if (o.status) o.status[s.traj] = status;
-        if (o.out_count) o.out_count[s.traj] = s.out_count;
-        return true;
-    }
-
-    /* Rk4::integrate prologue, rk4.rs:71-77 */
-    ODE_DEV static void init(State& s, const KernelArgsF32& a, long long t) {
-        s.traj = t;
-#pragma unroll
-        for (int c = 0; c < N; ++c) s.y[c] = __ldg(a.y0 + (size_t)c * a.n_traj + t);
-#pragma unroll
-        for (int c = 0; c < Sys::NP; ++c)
-            s.p[c] = a.params_per_traj ? __ldg(a.params + (size_t)c * a.n_traj + t) : __ldg(a.params + c);
-        if constexpr (Sys::NP == 0) s.p[0] = 0.0f;
-        s.x = a.x0;
-        s.num_eval = s.accepted = s.out_count = 0;
-        s.status = ODE_B200_OK;
-        push(a, s, s.x, s.y);
-        const float ns = ceilf((a.x_end - s.x) / a.step_size);
-        if (!(ns >= 0.0f) || ns > 4.0e9f) { /* to_usize().unwrap() panics in the reference */
-            s.status = ODE_B200_UNSUPPORTED_DOMAIN;
-            s.steps_left = 0;
-        } else {
-            s.steps_left = (unsigned long long)ns;
-        }
-    }
-
-    /* one Rk4::step + the loop body of integrate, rk4.rs:79-98,103-132 */
-    ODE_DEV static bool attempt(State& s, const KernelArgsF32& a) {
-        if (s.steps_left == 0) return finish(a, s);
-        const float step = a.step_size, half = step / 2.0f, x = s.x;
-        float k0[N], k1[N], k2[N], k3[N], buf[N], yn[N];
-        MathExact mx;
-        Sys::rhs(x, s.y, k0, s.p, mx);
-#pragma unroll
-        for (int i = 0; i < N; ++i) buf[i] = s.y[i] + k0[i] * half;
-        Sys::rhs(x + half, buf, k1, s.p, mx);
-#pragma unroll
-        for (int i = 0; i < N; ++i) buf[i] = s.y[i] + k1[i] * half;
-        Sys::rhs(x + half, buf, k2, s.p, mx);
-#pragma unroll
-        for (int i = 0; i < N; ++i) buf[i] = s.y[i] + k2[i] * step;
-        Sys::rhs(x + step, buf, k3, s.p, mx);
-        const float x_new = x + step;
-        const float h6 = step / 6.0f;
-#pragma unroll
-        for (int i = 0; i < N; ++i) yn[i] = s.y[i] + (((k0[i] + k1[i] * 2.0f) + k2[i] * 2.0f) + k3[i]) * h6;
-        bool stop = false;
-        if constexpr (Sys::HAS_SOLOUT) stop = Sys::solout(x_new, yn, k0, s.p);
-        s.x = x_new;
-#pragma unroll
-        for (int i = 0; i < N; ++i) s.y[i] = yn[i];
-        push(a, s, x_new, yn);
-        s.num_eval += 4;
-        s.accepted += 1;
-        s.steps_left -= 1;
-        if (stop) s.steps_left = 0;
-        if (s.steps_left == 0) return finish(a, s);
-        return false;
-    }
-};
-
-template <class Sys>
-__global__ void __launch_bounds__(128, 5) ode_rk4_f32_kernel(const __grid_constant__ KernelArgsF32 a) {
-    run_lanes_<Rk4StepperF32<Sys>>(a);
-}
-
 /* ============================================================================ kernels */
 template <class Stepper>
 __global__ void __launch_bounds__(Stepper::kThreads, Stepper::kMinBlocks) ode_step_loop_kernel(const __grid_constant__ KernelArgs a) {

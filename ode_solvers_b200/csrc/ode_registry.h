@@ -13,8 +13,8 @@ struct SystemEntry {
     int has_solout;
     /* [staged results: no, yes][method: Rk4, Dopri5, Dop853][out_type: Dense, Sparse, Continuous, Continuous8] */
     const void* kernels[2][3][4];
-    /* Rk4 with T = f32 (nullptr when the system's RHS is f64-only) */
-    const void* rk4_f32_kernel;
+    /* the steppers with T = f32 by method (nullptr when the system's RHS is f64-only) */
+    const void* f32_kernels[3];
     /* Dop853 with one trajectory per group of three lanes (ode_split.cuh), by out_type; nullptr: the
      * system has no split form and runs one trajectory per thread */
     const void* dop853_split_kernels[2][4]; /* [results staged through shared memory: no, yes][out_type] */

@@ -652,18 +652,46 @@ struct Dop853SplitStepper {
         }
 
         /* ---- dense-output coefficients (dop853.rs:398-480): whole warp when any lane accepted */
-        double rc[8][N];
+        /* Continuous8 with staged results: the coefficient rows go straight into the trajectory's shared-memory
+         * slot as they are produced instead of living in 96 registers until the end of the pass (ncu, rows kept
+         * in registers: 80 local-memory loads and 66 stores per pass, "long scoreboard" the second largest stall) */
+        constexpr bool kStream = CONT8 && STAGE;
+        double rc[kStream ? 4 : 8][N]; /* kStream: only the partial sums of rows 4..7 (as rc[0..3]) */
+        bool rec_y = false, rec_c = false;
+        double* slot = nullptr;
+        if constexpr (kStream) {
+            if (acc) {
+                rec_y = a.out.out_x != nullptr && (long long)s.c.out_count < a.out.out_cap;
+                rec_c = a.out.com_break != nullptr && (long long)s.c.com_count < a.out.com_cap;
+                if (rec_y || rec_c) {
+                    slot = slot_(L);
+                    slot_acquire_(L);
+                }
+            }
+        }
+        constexpr int kHi = kStream ? 0 : 4; /* where rows 4..7 live in rc */
         if constexpr (DENSE || CONT8) {
             if (__any_sync(kFullMask, acc)) {
                 double yy[N], p15[N], p16[N], k14[N], k15[N], k16[N];
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
-                    rc[0][i] = s.y[i];
                     const double ydiff = y8[i] - s.y[i];
-                    rc[1][i] = ydiff;
                     const double bspl = k[0][i] * h - ydiff;
-                    rc[2][i] = bspl;
-                    rc[3][i] = (ydiff - knew[i] * h) - bspl;
+                    const double c3 = (ydiff - knew[i] * h) - bspl;
+                    if constexpr (kStream) {
+                        if (rec_c) {
+                            double* b = slot + SS::gcomp(L.role, i);
+                            b[0 * NF] = s.y[i];
+                            b[1 * NF] = ydiff;
+                            b[2 * NF] = bspl;
+                            b[3 * NF] = c3;
+                        }
+                    } else {
+                        rc[0][i] = s.y[i];
+                        rc[1][i] = ydiff;
+                        rc[2][i] = bspl;
+                        rc[3][i] = c3;
+                    }
                     const double k0 = k[0][i], k5 = k[5][i], k6 = k[6][i], k7 = k[7][i], k8 = k[8][i], k9 = k[9][i],
                                  k10 = k[10][i], k11 = k[11][i], kn = knew[i];
                     static_for<0, 4>([&](auto R) {
@@ -676,7 +704,7 @@ struct Dop853SplitStepper {
                         v = v + k9 * c_dp8_d[r][9];
                         v = v + k10 * c_dp8_d[r][10];
                         v = v + k11 * c_dp8_d[r][11];
-                        rc[4 + r][i] = v;
+                        rc[kHi + r][i] = v;
                     });
                     yy[i] = s.y[i] + (((((((k0 * c_dp8_a[13][0] + k6 * c_dp8_a[13][6]) + k7 * c_dp8_a[13][7]) +
                                            k8 * c_dp8_a[13][8]) +
@@ -725,10 +753,15 @@ struct Dop853SplitStepper {
                     const double kn = knew[i], ka = k14[i], kb = k15[i], kc = k16[i];
                     static_for<0, 4>([&](auto R) {
                         constexpr int r = decltype(R)::value;
-                        rc[4 + r][i] = ((((rc[4 + r][i] + kn * c_dp8_d[r][12]) + ka * c_dp8_d[r][13]) +
-                                         kb * c_dp8_d[r][14]) +
-                                        kc * c_dp8_d[r][15]) *
-                                       h;
+                        const double v = ((((rc[kHi + r][i] + kn * c_dp8_d[r][12]) + ka * c_dp8_d[r][13]) +
+                                           kb * c_dp8_d[r][14]) +
+                                          kc * c_dp8_d[r][15]) *
+                                         h;
+                        if constexpr (kStream) {
+                            if (rec_c) slot[(4 + r) * NF + SS::gcomp(L.role, i)] = v;
+                        } else {
+                            rc[4 + r][i] = v;
+                        }
                     });
                 }
             }
@@ -777,6 +810,27 @@ struct Dop853SplitStepper {
                         s.xd += cfg.dx;
                     }
                 }
+            } else if constexpr (kStream) { /* the sample row, then the slot leaves (see push_step) */
+                const ode_b200_outputs& o = a.out;
+                const size_t qy = (size_t)s.traj * (size_t)a.out_pitch + s.c.out_count;
+                const size_t qc = (size_t)s.traj * (size_t)a.com_pitch + s.c.com_count;
+                if (rec_y || rec_c) {
+#pragma unroll
+                    for (int c = 0; c < N; ++c) slot[8 * NF + SS::gcomp(L.role, c)] = s.y[c];
+                    slot_release_(L);
+                    if (L.role == 0u) {
+                        if (rec_y) o.out_x[qy] = s.x;
+                        if (rec_c) {
+                            o.com_break[qc] = fabs(s.x);
+                            o.com_step[qc] = s.h_old;
+                            bulk_(o.com_coef + qc * (8 * NF), slot, 8 * NF * 8);
+                        }
+                        if (rec_y) bulk_(o.out_y + qy * NF, slot + 8 * NF, NF * 8);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+                s.c.out_count += 1;
+                s.c.com_count += 1;
             } else if constexpr (CONT8) {
                 push_step(a, s, L, s.x, s.y, fabs(s.x), s.h_old, rc);
             } else {

@@ -39,6 +39,18 @@ typedef struct ode_oracle_system {
     ode_oracle_solout_fn solout; /* NULL = default `false` (dop_shared.rs:39-41) */
 } ode_oracle_system;
 
+/* the same with T = f32, for the systems whose RHS has an f32 form */
+typedef void (*ode_oracle_rhs32_fn)(float x, const float* y, float* dy, const float* p);
+typedef int (*ode_oracle_solout32_fn)(float x, const float* y, const float* dy, const float* p);
+typedef struct ode_oracle_system32 {
+    const char* name;
+    int dim;
+    int n_params;
+    ode_oracle_rhs32_fn rhs;
+    ode_oracle_solout32_fn solout;
+} ode_oracle_system32;
+const ode_oracle_system32* ode_oracle_system32_by_name(const char* name);
+
 const ode_oracle_system* ode_oracle_system_by_name(const char* name);
 int ode_oracle_system_count(void);
 const ode_oracle_system* ode_oracle_system_at(int i);
@@ -61,6 +73,21 @@ int ode_oracle_config_rk4(double x, double x_end, double step_size, ode_b200_con
 int ode_oracle_integrate_batch(const char* system, const ode_b200_config* cfg, int64_t n_traj,
                                const double* y0, const double* params, int params_per_traj,
                                const ode_b200_outputs* out, int n_threads);
+
+/* The three steppers with T = f32 (the crate is generic over FloatNumber, src/dop_shared.rs:52-77): the same
+ * source (ode_oracle_core.inc) instantiated for float, libm powf/sqrtf. Constructors like the f64 ones with
+ * every literal rounded to f32 and every operation in f32 (Q3: Dopri5::new takes uround = f32::EPSILON). */
+int ode_oracle_config_new_f32(int method, float x, float x_end, float dx, float rtol, float atol,
+                              ode_b200_config_f32* out);
+int ode_oracle_config_from_param_f32(int method, float x, float x_end, float dx, float rtol, float atol,
+                                     float safety_factor, float beta, float fac_min, float fac_max, float h_max,
+                                     float h, uint32_t n_max, uint32_t n_stiff, int out_type,
+                                     ode_b200_config_f32* out);
+int ode_oracle_config_rk4_f32(float x, float x_end, float step_size, ode_b200_config_f32* out);
+int ode_oracle_integrate_batch_f32(const char* system, const ode_b200_config_f32* cfg, int64_t n_traj,
+                                   const float* y0, const float* params, int params_per_traj,
+                                   const ode_b200_outputs_f32* out, int n_threads);
+float ode_oracle_powf(float x, float y);
 
 /* Rk4 with T = f32 (src/rk4.rs generic over FloatNumber, src/dop_shared.rs:74), for the systems
  * whose RHS has an f32 form. Same arguments as ode_b200_rk4_f32_integrate_batch. */

@@ -152,9 +152,6 @@ const ode_oracle_system* ode_oracle_system_by_name(const char* name) {
 /* ------------------------------------------------------------------ f32 forms (T = f32) */
 /* the same statements with every operation in single precision, as rustc compiles the generic
  * code for T = f32 (examples/bouncing_ball.rs:15,77-86 is written for f32) */
-typedef void (*rhs32_fn)(float x, const float* y, float* dy, const float* p);
-typedef int (*solout32_fn)(float x, const float* y, const float* dy, const float* p);
-
 static void lorenz_rhs32(float x, const float* y, float* dy, const float* p) {
     (void)x;
     dy[0] = p[0] * (y[1] - y[0]);
@@ -186,83 +183,14 @@ static void test_rk4_2_rhs32(float x, const float* y, float* dy, const float* p)
     dy[0] = -2.0f * x - y[0];
 }
 
-typedef struct {
-    const char* name;
-    int dim, n_params;
-    rhs32_fn rhs;
-    solout32_fn solout;
-} sys32_t;
-static const sys32_t SYSTEMS32[] = {
+static const ode_oracle_system32 SYSTEMS32[] = {
     {"lorenz", 3, 3, lorenz_rhs32, 0},         {"robertson", 3, 3, robertson_rhs32, 0},
     {"bouncing_ball", 3, 1, ball_rhs32, ball_solout32}, {"test_rk4_1", 1, 0, test_rk4_1_rhs32, 0},
     {"test_rk4_2", 1, 0, test_rk4_2_rhs32, 0},
 };
-
-/* Rk4::integrate / step with T = f32, rk4.rs:71-143 */
-int ode_oracle_rk4_f32_integrate_batch(const char* system, float x0, float x_end, float step, int64_t n,
-                                       const float* y0, const float* params, int per_traj,
-                                       const ode_b200_outputs_f32* out, int n_threads) {
-    const sys32_t* S = 0;
+const ode_oracle_system32* ode_oracle_system32_by_name(const char* name) {
+    if (!name) return 0;
     for (unsigned q = 0; q < sizeof(SYSTEMS32) / sizeof(SYSTEMS32[0]); ++q)
-        if (system && !strcmp(SYSTEMS32[q].name, system)) S = &SYSTEMS32[q];
-    if (!S || !out || n < 0 || !y0) return -1;
-    const int d = S->dim;
-    (void)n_threads;
-#pragma omp parallel for schedule(dynamic, 64)
-    for (int64_t i = 0; i < n; ++i) {
-        float y[ODE_B200_MAX_DIM], p[ODE_B200_MAX_PARAMS + 1], k[4][ODE_B200_MAX_DIM], buf[ODE_B200_MAX_DIM],
-            yn[ODE_B200_MAX_DIM];
-        for (int c = 0; c < d; ++c) y[c] = y0[(size_t)c * n + i];
-        for (int c = 0; c < S->n_params; ++c) p[c] = per_traj ? params[(size_t)c * n + i] : params[c];
-        memset(k, 0, sizeof(k));
-        float x = x0;
-        const float half = step / 2.0f;
-        uint32_t num_eval = 0, accepted = 0, count = 0;
-        int status = ODE_B200_OK;
-#define PUSH32(xx, yy)                                                                          \
-    do {                                                                                        \
-        if (out->out_x && out->out_y && (int64_t)count < out->out_cap) {                        \
-            out->out_x[(size_t)i * out->out_cap + count] = (xx);                                \
-            for (int c = 0; c < d; ++c) out->out_y[((size_t)i * out->out_cap + count) * d + c] = (yy)[c]; \
-        }                                                                                       \
-        ++count;                                                                                \
-    } while (0)
-        PUSH32(x, y);
-        float ns = ceilf((x_end - x) / step);
-        if (!(ns >= 0.0f) || ns > 4.0e9f) {
-            status = ODE_B200_UNSUPPORTED_DOMAIN;
-            ns = 0.0f;
-        }
-        const uint64_t num_steps = (uint64_t)ns;
-        for (uint64_t it = 0; it < num_steps; ++it) {
-            S->rhs(x, y, k[0], p);
-            for (int c = 0; c < d; ++c) buf[c] = y[c] + k[0][c] * half;
-            S->rhs(x + half, buf, k[1], p);
-            for (int c = 0; c < d; ++c) buf[c] = y[c] + k[1][c] * half;
-            S->rhs(x + half, buf, k[2], p);
-            for (int c = 0; c < d; ++c) buf[c] = y[c] + k[2][c] * step;
-            S->rhs(x + step, buf, k[3], p);
-            const float x_new = x + step;
-            for (int c = 0; c < d; ++c)
-                yn[c] = y[c] + (((k[0][c] + k[1][c] * 2.0f) + k[2][c] * 2.0f) + k[3][c]) * (step / 6.0f);
-            const int stop = S->solout ? S->solout(x_new, yn, k[0], p) : 0;
-            x = x_new;
-            for (int c = 0; c < d; ++c) y[c] = yn[c];
-            PUSH32(x_new, yn);
-            num_eval += 4;
-            accepted += 1;
-            if (stop) break;
-        }
-#undef PUSH32
-        if (status == ODE_B200_OK && out->out_cap > 0 && (int64_t)count > out->out_cap)
-            status = ODE_B200_OUTPUT_CAPACITY_EXCEEDED;
-        if (out->y_final)
-            for (int c = 0; c < d; ++c) out->y_final[(size_t)c * n + i] = y[c];
-        if (out->x_final) out->x_final[i] = x;
-        if (out->num_eval) out->num_eval[i] = num_eval;
-        if (out->accepted) out->accepted[i] = accepted;
-        if (out->status) out->status[i] = status;
-        if (out->out_count) out->out_count[i] = count;
-    }
+        if (!strcmp(SYSTEMS32[q].name, name)) return &SYSTEMS32[q];
     return 0;
 }

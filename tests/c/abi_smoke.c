@@ -28,10 +28,18 @@ int main(void) {
     OFF(ode_b200_outputs, out_x); OFF(ode_b200_outputs, out_y); OFF(ode_b200_outputs, out_count);
     OFF(ode_b200_outputs, com_cap); OFF(ode_b200_outputs, com_lower); OFF(ode_b200_outputs, com_break);
     OFF(ode_b200_outputs, com_step); OFF(ode_b200_outputs, com_coef); OFF(ode_b200_outputs, com_count);
-    OFF(ode_b200_outputs_f32, y_final); OFF(ode_b200_outputs_f32, x_final);
-    OFF(ode_b200_outputs_f32, num_eval); OFF(ode_b200_outputs_f32, accepted);
-    OFF(ode_b200_outputs_f32, status); OFF(ode_b200_outputs_f32, out_cap);
+    OFF(ode_b200_outputs_f32, y_final); OFF(ode_b200_outputs_f32, x_final); OFF(ode_b200_outputs_f32, h_next);
+    OFF(ode_b200_outputs_f32, num_eval); OFF(ode_b200_outputs_f32, accepted); OFF(ode_b200_outputs_f32, rejected);
+    OFF(ode_b200_outputs_f32, n_step); OFF(ode_b200_outputs_f32, status); OFF(ode_b200_outputs_f32, out_cap);
     OFF(ode_b200_outputs_f32, out_x); OFF(ode_b200_outputs_f32, out_y); OFF(ode_b200_outputs_f32, out_count);
+    OFF(ode_b200_outputs_f32, com_cap); OFF(ode_b200_outputs_f32, com_lower); OFF(ode_b200_outputs_f32, com_break);
+    OFF(ode_b200_outputs_f32, com_step); OFF(ode_b200_outputs_f32, com_coef); OFF(ode_b200_outputs_f32, com_count);
+    OFF(ode_b200_config_f32, method); OFF(ode_b200_config_f32, out_type); OFF(ode_b200_config_f32, x0);
+    OFF(ode_b200_config_f32, x_end); OFF(ode_b200_config_f32, dx); OFF(ode_b200_config_f32, rtol);
+    OFF(ode_b200_config_f32, atol); OFF(ode_b200_config_f32, safety_factor); OFF(ode_b200_config_f32, alpha);
+    OFF(ode_b200_config_f32, beta); OFF(ode_b200_config_f32, fac_min); OFF(ode_b200_config_f32, fac_max);
+    OFF(ode_b200_config_f32, h_max); OFF(ode_b200_config_f32, h0); OFF(ode_b200_config_f32, uround);
+    OFF(ode_b200_config_f32, step_size); OFF(ode_b200_config_f32, n_max); OFF(ode_b200_config_f32, n_stiff);
     printf("sizeof_outputs_f32 %zu\n", sizeof(ode_b200_outputs_f32));
     if (ode_b200_device_count() == 0) {
         ode_b200_ctx* ctx = ode_b200_create(0);

@@ -32,6 +32,9 @@ def lib():
             build()
         l = C.CDLL(ORACLE_LIB)
         _abi.declare_config_fns(l, "ode_oracle_")
+        _abi.declare_config_fns_f32(l, "ode_oracle_")
+        l.ode_oracle_powf.argtypes = [C.c_float, C.c_float]
+        l.ode_oracle_powf.restype = C.c_float
         l.ode_oracle_integrate_batch.argtypes = [C.c_char_p, C.POINTER(_abi.Config), C.c_int64, C.c_void_p,
                                                  C.c_void_p, C.c_int, C.POINTER(_abi.Outputs), C.c_int]
         l.ode_oracle_integrate_batch.restype = C.c_int
@@ -109,6 +112,50 @@ def integrate_batch(system, cfg, y0, params=None, out_cap=0, com_cap=0, n_thread
     s = out.struct()
     rc = lib().ode_oracle_integrate_batch(system.encode(), C.byref(cfg), n, y0.ctypes.data, pp, per_traj,
                                           C.byref(s), n_threads)
+    assert rc == 0, rc
+    return out
+
+
+def config_new_f32(method, x, x_end, dx, rtol, atol, out_type=None):
+    c = _abi.ConfigF32()
+    assert lib().ode_oracle_config_new_f32(method, x, x_end, dx, rtol, atol, C.byref(c)) == 0
+    if out_type is not None:
+        c.out_type = out_type
+    return c
+
+
+def config_from_param_f32(method, x, x_end, dx, rtol, atol, safety, beta, fac_min, fac_max, h_max, h, n_max,
+                          n_stiff, out_type):
+    c = _abi.ConfigF32()
+    assert lib().ode_oracle_config_from_param_f32(method, x, x_end, dx, rtol, atol, safety, beta, fac_min, fac_max,
+                                                  h_max, h, n_max, n_stiff, out_type, C.byref(c)) == 0
+    return c
+
+
+def config_rk4_f32(x, x_end, step):
+    c = _abi.ConfigF32()
+    assert lib().ode_oracle_config_rk4_f32(x, x_end, step, C.byref(c)) == 0
+    return c
+
+
+def integrate_batch_f32(system, cfg, y0, params=None, out_cap=0, com_cap=0, n_threads=0):
+    """the three steppers with T = f32; y0: [dim][n] float32"""
+    dim, n_params = system_info(system)
+    y0 = np.ascontiguousarray(np.asarray(y0, dtype=np.float32).reshape(dim, -1))
+    n = y0.shape[1]
+    per_traj, pp = 0, None
+    if n_params:
+        params = np.ascontiguousarray(np.asarray(params, dtype=np.float32))
+        per_traj = int(params.ndim == 2)
+        pp = params.ctypes.data
+    m = 5 if cfg.method == _abi.DOPRI5 else 8
+    out = _abi.HostOutputsF32(n, dim, out_cap, com_cap, m)
+    s = out.struct()
+    f = lib().ode_oracle_integrate_batch_f32
+    f.argtypes = [C.c_char_p, C.POINTER(_abi.ConfigF32), C.c_int64, C.c_void_p, C.c_void_p, C.c_int,
+                  C.POINTER(_abi.OutputsF32), C.c_int]
+    f.restype = C.c_int
+    rc = f(system.encode(), C.byref(cfg), n, y0.ctypes.data, pp, per_traj, C.byref(s), n_threads)
     assert rc == 0, rc
     return out
 

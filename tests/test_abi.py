@@ -22,7 +22,7 @@ def test_every_declared_symbol_is_exported():
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]
     assert not missing, missing
     assert declared == set(_abi.ABI_SYMBOLS), declared ^ set(_abi.ABI_SYMBOLS)
-    assert lib.ode_b200_abi_version() == 1
+    assert lib.ode_b200_abi_version() == 2  # 2: the f32 mirror structs + entries, ode_b200_set_lane_split
 
 
 def test_builtin_systems_match_the_oracle_registry():

@@ -31,7 +31,8 @@ def test_c_header_links_and_struct_layout(tmp_path):
     assert int(f[3]) == C.sizeof(_abi.Config) and int(f[5]) == C.sizeof(_abi.Outputs)
     # every field: offset and size of the C struct == the ctypes mirror (tests/oracle.py shares these mirrors
     # with the product wrapper, so a layout bug would otherwise cancel on both sides of a parity test)
-    mirrors = {"ode_b200_config": _abi.Config, "ode_b200_outputs": _abi.Outputs, "ode_b200_outputs_f32": _abi.OutputsF32}
+    mirrors = {"ode_b200_config": _abi.Config, "ode_b200_outputs": _abi.Outputs, "ode_b200_outputs_f32": _abi.OutputsF32,
+               "ode_b200_config_f32": _abi.ConfigF32}
     seen = {k: [] for k in mirrors}
     for line in out.splitlines():
         if line.startswith("offset "):
