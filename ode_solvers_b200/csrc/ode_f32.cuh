@@ -145,8 +145,8 @@ struct F32Stepper {
         if (o.status) o.status[t] = status;
         if (o.out_count) o.out_count[t] = s.c.out_count;
         if (o.com_count) o.com_count[t] = s.c.com_count;
-        if (o.com_lower)
-            o.com_lower[t] = (METHOD == ODE_B200_DOPRI5) ? a.cfg.x0 : 0.0f; /* set_lower_bound, dopri5.rs:279-281 */
+        if (o.com_lower) /* set_lower_bound, dopri5.rs:279-281 (never reached when `% n_stiff` would panic) */
+            o.com_lower[t] = (METHOD == ODE_B200_DOPRI5 && a.cfg.n_stiff != 0) ? a.cfg.x0 : 0.0f;
         return true;
     }
 

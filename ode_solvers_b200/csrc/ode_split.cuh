@@ -181,7 +181,15 @@ struct Dop853SplitStepper {
     static constexpr int kSlotDoubles = 9 * NF;
     static constexpr bool DENSE = OUT == ODE_B200_OUT_DENSE;
     static constexpr bool CONT8 = OUT == ODE_B200_OUT_CONTINUOUS8;
-    static constexpr int kThreads = (DENSE || CONT8) ? 256 : ODE_B200_LOCK_THREADS; /* as the n = 6 lockstep kernels */
+    /* one lockstep CTA per SM like the n = 6 kernels: 12 warps at 168 registers, 8 warps with all 255 when the
+     * dense-output coefficients are live as well (-D overrides for measurements) */
+#ifndef ODE_B200_SPLIT_THREADS_SPARSE
+#define ODE_B200_SPLIT_THREADS_SPARSE ODE_B200_LOCK_THREADS
+#endif
+#ifndef ODE_B200_SPLIT_THREADS_DENSE
+#define ODE_B200_SPLIT_THREADS_DENSE 256
+#endif
+    static constexpr int kThreads = (DENSE || CONT8) ? ODE_B200_SPLIT_THREADS_DENSE : ODE_B200_SPLIT_THREADS_SPARSE;
     static constexpr int kSlotsPerWarp = 10;
     static constexpr int kRefillIdle = ODE_B200_REFILL_IDLE;
     static_assert(!SS::HAS_SOLOUT, "solout of a split system is not implemented");
