@@ -20,5 +20,5 @@ for o in $SRC/build/*.o; do
   b=$(basename $o)
   if [ -f $B/$b ]; then OBJS="$OBJS $B/$b"; else OBJS="$OBJS $o"; fi
 done
-/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $ROOT/variants/libode_$NAME.so $OBJS -cudart static -ldl -lpthread
+/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $ROOT/variants/libode_$NAME.so $OBJS -cudart static -ldl -lpthread $VARIANT_LINK_FLAGS
 echo built $ROOT/variants/libode_$NAME.so
