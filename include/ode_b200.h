@@ -299,6 +299,13 @@ int ode_b200_rk4_f32_integrate_batch(ode_b200_ctx* ctx, int sys_id, float x, flo
 /* kernel scheduling knob: 1 (default) = persistent kernel with lane refill from a work
  * queue; 0 = static one-thread-per-trajectory launch (kept for the ablation in DESIGN.md) */
 int ode_b200_set_work_queue(ode_b200_ctx* ctx, int enabled);
+/* host-buffer entry: pipeline of upload, integration and copy-back. chunk_log2 = 16 (default): the batch is
+ * cut into chunks of 2^16 trajectories; the kernel starts before its inputs have arrived (lanes wait for
+ * their chunk), and the per-trajectory results of a finished chunk are copied back while the rest of the
+ * batch is still being integrated. Used when the batch has at least two chunks and the caller's
+ * per-trajectory result arrays are pinned host memory (cudaHostAlloc / cudaHostRegister); 0 switches it off
+ * (upload, kernel, copy-back one after the other, or zero-copy result stores: ode_b200_set_zero_copy). */
+int ode_b200_set_pipeline(ode_b200_ctx* ctx, int chunk_log2);
 /* large states: 1 (default) = Dop853 runs one trajectory per group of three lanes for the systems that
  * have that form (threebody18), the state and stage vectors dealt out component-wise so that they stay in
  * registers; 0 = one trajectory per thread like everything else (kept for the ablation; same bits) */

@@ -178,7 +178,7 @@ ABI_SYMBOLS = [
     "ode_b200_system_name", "ode_b200_system_from_source", "ode_b200_system_compile",
     "ode_b200_config_new", "ode_b200_config_from_param", "ode_b200_config_rk4",
     "ode_b200_create", "ode_b200_destroy", "ode_b200_last_kernel_ms", "ode_b200_launch_count",
-    "ode_b200_set_zero_copy", "ode_b200_set_lane_split",
+    "ode_b200_set_zero_copy", "ode_b200_set_lane_split", "ode_b200_set_pipeline",
     "ode_b200_stream",
     "ode_b200_integrate_batch", "ode_b200_integrate_batch_device", "ode_b200_integrate_batch_multi",
     "ode_b200_rk4_f32_integrate_batch", "ode_b200_integrate_batch_f32",
@@ -276,6 +276,8 @@ def load():
     lib.ode_b200_set_zero_copy.restype = C.c_int
     lib.ode_b200_set_lane_split.argtypes = [C.c_void_p, C.c_int]
     lib.ode_b200_set_lane_split.restype = C.c_int
+    lib.ode_b200_set_pipeline.argtypes = [C.c_void_p, C.c_int]
+    lib.ode_b200_set_pipeline.restype = C.c_int
     lib.ode_b200_com_evaluate.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int64,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]

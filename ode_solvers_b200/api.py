@@ -119,6 +119,11 @@ class Context:
         or go through device buffers and DMA copies (better when several GPUs share the host's PCIe)"""
         _check(self._lib.ode_b200_set_zero_copy(self.handle, int(bool(enabled))), "set_zero_copy")
 
+    def set_pipeline(self, chunk_log2):
+        """host-buffer entry: chunked upload / integrate / copy-back pipeline (default 16 = 65536 trajectories per
+        chunk; 0 = off)"""
+        _check(self._lib.ode_b200_set_pipeline(self.handle, int(chunk_log2)), "set_pipeline")
+
     def set_lane_split(self, enabled):
         """large states (threebody18 / Dop853): one trajectory per group of three lanes (default) or per thread"""
         _check(self._lib.ode_b200_set_lane_split(self.handle, int(bool(enabled))), "set_lane_split")

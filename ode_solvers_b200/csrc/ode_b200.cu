@@ -222,6 +222,7 @@ struct DevBuf {
 /* work-queue heads per context: launch k uses word k % kQueueSlots (more than kQueueSlots launches of
  * one context in flight at once is not supported; include/ode_b200.h says so) */
 static constexpr unsigned kQueueSlots = 64;
+static constexpr int kPipeMaxChunks = 4096;
 
 struct ode_b200_ctx {
     int device = 0;
@@ -232,6 +233,13 @@ struct ode_b200_ctx {
     int use_queue = 1;
     int zero_copy = 1; /* per-trajectory results straight into pinned host arrays (ode_b200_set_zero_copy) */
     int lane_split = 1; /* large states: one trajectory per group of three lanes where the system has that form */
+    /* host pipeline of the host-buffer entry (ode_kernel_args.h): log2 of the chunk size, 0 = off */
+    int pipeline_shift = 16;
+    cudaStream_t up_stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_pipe = nullptr;
+    unsigned* pipe_flags_host = nullptr; /* mapped pinned: one word per chunk + one constant 1 at [kPipeMaxChunks] */
+    unsigned* pipe_flags_dev = nullptr;  /* its device alias */
+    DevBuf pipe_dev;                     /* upload_ready[chunks], chunk_done[chunks] */
     unsigned long long* queue = nullptr;
     uint64_t launches = 0;
     double last_ms = 0.0;
@@ -267,7 +275,14 @@ extern "C" ode_b200_ctx* ode_b200_create(int device) {
               cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess &&
               cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess &&
-              cudaMalloc((void**)&c->queue, kQueueSlots * sizeof(unsigned long long)) == cudaSuccess;
+              cudaMalloc((void**)&c->queue, kQueueSlots * sizeof(unsigned long long)) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_pipe, cudaEventDisableTiming) == cudaSuccess &&
+              cudaHostAlloc((void**)&c->pipe_flags_host, (kPipeMaxChunks + 1) * sizeof(unsigned), cudaHostAllocMapped) ==
+                  cudaSuccess &&
+              cudaHostGetDevicePointer((void**)&c->pipe_flags_dev, c->pipe_flags_host, 0) == cudaSuccess;
+    if (ok) c->pipe_flags_host[kPipeMaxChunks] = 1u;
     if (!ok) {
         fail(ODE_B200_ERR_CUDA, std::string("context creation failed: ") + cudaGetErrorString(cudaGetLastError()));
         delete c;
@@ -287,6 +302,11 @@ extern "C" void ode_b200_destroy(ode_b200_ctx* c) {
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->queue) cudaFree(c->queue);
+    if (c->pipe_dev.p) cudaFree(c->pipe_dev.p);
+    if (c->pipe_flags_host) cudaFreeHost(c->pipe_flags_host);
+    if (c->up_stream) cudaStreamDestroy(c->up_stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->ev_pipe) cudaEventDestroy(c->ev_pipe);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -305,6 +325,13 @@ extern "C" void* ode_b200_stream(const ode_b200_ctx* c) { return c ? (void*)c->s
 extern "C" int ode_b200_set_zero_copy(ode_b200_ctx* c, int enabled) {
     if (!c) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
     c->zero_copy = enabled ? 1 : 0;
+    return ODE_B200_SUCCESS;
+}
+extern "C" int ode_b200_set_pipeline(ode_b200_ctx* c, int chunk_log2) {
+    if (!c) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    if (chunk_log2 != 0 && (chunk_log2 < 8 || chunk_log2 > 24))
+        return fail(ODE_B200_ERR_INVALID_ARGUMENT, "set_pipeline: chunk_log2 must be 0 (off) or 8..24");
+    c->pipeline_shift = chunk_log2;
     return ODE_B200_SUCCESS;
 }
 extern "C" int ode_b200_set_lane_split(ode_b200_ctx* c, int enabled) {
@@ -358,9 +385,16 @@ __global__ void fill_unsupported_kernel(KernelArgs a, int dim) {
 }
 
 /* enqueue the step-loop kernel for device-resident inputs/outputs on `stream` */
+struct PipeArgs { /* host pipeline of this launch (ode_kernel_args.h); shift == 0: off */
+    int shift = 0;
+    const unsigned* upload_ready = nullptr;
+    unsigned* chunk_done = nullptr;
+    unsigned* chunk_flag = nullptr;
+};
+
 static int launch_device(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg, int64_t n, const double* y0,
                          const double* params, int per_traj, const ode_b200_outputs* out, long long out_pitch,
-                         long long com_pitch, cudaStream_t stream) {
+                         long long com_pitch, cudaStream_t stream, const PipeArgs* pipe = nullptr) {
     SysInfo s;
     if (!sys_info(sys_id, &s)) return fail(ODE_B200_ERR_UNKNOWN_SYSTEM, "bad sys_id");
     if (int rc = validate(cfg, s, n, y0, params, out)) return rc;
@@ -397,6 +431,12 @@ static int launch_device(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg
     ka.com_pitch = com_pitch > 0 ? com_pitch : out->com_cap;
     if (ka.out.out_cap == 0) ka.out.out_x = ka.out.out_y = nullptr;
     if (ka.out.com_cap == 0) ka.out.com_break = ka.out.com_step = ka.out.com_coef = nullptr;
+    if (pipe && pipe->shift > 0) {
+        ka.chunk_shift = pipe->shift;
+        ka.upload_ready = pipe->upload_ready;
+        ka.chunk_done = pipe->chunk_done;
+        ka.chunk_flag = pipe->chunk_flag;
+    }
 
     /* large states (ode_split.cuh): Dop853 with one trajectory per group of three lanes */
     const void* split_fn = nullptr;
@@ -511,7 +551,9 @@ static int integrate_range(ode_b200_ctx* c, int sys_id, const ode_b200_config* c
     const int rc = integrate_range_impl(c, sys_id, cfg, n_total, lo, hi, y0, params, per_traj, out);
     if (rc != ODE_B200_SUCCESS && c && c->stream) {
         const std::string keep = g_last_error;
+        cudaStreamSynchronize(c->up_stream);
         cudaStreamSynchronize(c->stream);
+        cudaStreamSynchronize(c->copy_stream);
         cudaGetLastError();
         g_last_error = keep;
     }
@@ -531,13 +573,49 @@ static int integrate_range_impl(ode_b200_ctx* c, int sys_id, const ode_b200_conf
     const int m = cfg->method == ODE_B200_DOPRI5 ? 5 : 8;
     cudaStream_t st = c->stream;
 
+    /* Host pipeline (ode_kernel_args.h): with at least two chunks of work and pinned per-trajectory result
+     * arrays the kernel is launched first, the inputs are uploaded chunk by chunk behind it, and finished
+     * chunks are copied back while the rest is still being integrated; what is left exposed is the first
+     * chunk's upload and the last chunk's copy. Measured on B200, ms per call (kernel alone / one-shot copies /
+     * zero-copy result stores / pipeline): see DESIGN.md section 5. */
+    const int shift = c->pipeline_shift;
+    const int64_t n_chunks = shift > 0 ? (n + ((int64_t)1 << shift) - 1) >> shift : 0;
+    bool pipe = shift > 0 && n_chunks >= 2 && n_chunks <= kPipeMaxChunks &&
+                !(cfg->method != ODE_B200_RK4 && cfg->n_stiff == 0);
+    if (pipe) {
+        const void* ptrs[] = {out->y_final, out->x_final, out->h_next,    out->num_eval,  out->accepted, out->rejected,
+                              out->n_step,  out->status,  out->out_count, out->com_count, out->com_lower};
+        bool any = false;
+        for (const void* q : ptrs)
+            if (q) {
+                any = true;
+                cudaPointerAttributes at;
+                if (cudaPointerGetAttributes(&at, q) != cudaSuccess || at.type != cudaMemoryTypeHost) pipe = false;
+                cudaGetLastError();
+            }
+        pipe = pipe && any;
+    }
+    PipeArgs pa;
+    if (pipe) {
+        if (ensure(c, c->pipe_dev, (size_t)n_chunks * 2 * sizeof(unsigned))) return ODE_B200_ERR_CUDA;
+        pa.shift = shift;
+        pa.upload_ready = (const unsigned*)c->pipe_dev.p;
+        pa.chunk_done = (unsigned*)c->pipe_dev.p + n_chunks;
+        pa.chunk_flag = c->pipe_flags_dev;
+        for (int64_t k = 0; k < n_chunks; ++k) c->pipe_flags_host[k] = 0u;
+        CUDA_TRY(cudaMemsetAsync(c->pipe_dev.p, 0, (size_t)n_chunks * 2 * sizeof(unsigned), st));
+        CUDA_TRY(cudaEventRecord(c->ev_pipe, st));
+        CUDA_TRY(cudaStreamWaitEvent(c->up_stream, c->ev_pipe, 0));
+    }
+
     if (ensure(c, c->y0, d * n * 8)) return ODE_B200_ERR_CUDA;
-    CUDA_TRY(cudaMemcpy2DAsync(c->y0.p, n * 8, y0 + lo, n_total * 8, n * 8, d, cudaMemcpyHostToDevice, st));
+    if (!pipe) CUDA_TRY(cudaMemcpy2DAsync(c->y0.p, n * 8, y0 + lo, n_total * 8, n * 8, d, cudaMemcpyHostToDevice, st));
     if (np) {
         if (per_traj) {
             if (ensure(c, c->params, np * n * 8)) return ODE_B200_ERR_CUDA;
-            CUDA_TRY(cudaMemcpy2DAsync(c->params.p, n * 8, params + lo, n_total * 8, n * 8, np,
-                                       cudaMemcpyHostToDevice, st));
+            if (!pipe)
+                CUDA_TRY(cudaMemcpy2DAsync(c->params.p, n * 8, params + lo, n_total * 8, n * 8, np,
+                                           cudaMemcpyHostToDevice, st));
         } else {
             if (ensure(c, c->params, np * 8)) return ODE_B200_ERR_CUDA;
             CUDA_TRY(cudaMemcpyAsync(c->params.p, params, np * 8, cudaMemcpyHostToDevice, st));
@@ -563,7 +641,7 @@ static int integrate_range_impl(ode_b200_ctx* c, int sys_id, const ode_b200_conf
     {                                                                                          \
         ++zc_bit;                                                                              \
         if (out->field) {                                                                      \
-            void* mp = c->zero_copy ? mapped_host_ptr(out->field) : nullptr;                   \
+            void* mp = (c->zero_copy && !pipe) ? mapped_host_ptr(out->field) : nullptr;        \
             if (mp) {                                                                          \
                 dv.field = (decltype(dv.field))((char*)mp + (size_t)lo * (elem_bytes));        \
                 zero_copy |= 1u << zc_bit;                                                     \
@@ -574,7 +652,7 @@ static int integrate_range_impl(ode_b200_ctx* c, int sys_id, const ode_b200_conf
         }                                                                                      \
     }
     if (out->y_final) {
-        void* mp = (c->zero_copy && lo == 0 && n == n_total) ? mapped_host_ptr(out->y_final) : nullptr;
+        void* mp = (c->zero_copy && !pipe && lo == 0 && n == n_total) ? mapped_host_ptr(out->y_final) : nullptr;
         if (mp) {
             dv.y_final = (double*)mp;
             zero_copy |= 1u;
@@ -610,10 +688,73 @@ static int integrate_range_impl(ode_b200_ctx* c, int sys_id, const ode_b200_conf
     }
 #undef WANT
     if (int rc = launch_device(c, sys_id, cfg, n, (const double*)c->y0.p, (const double*)c->params.p, per_traj,
-                               &dv, (long long)pitch, (long long)cpitch, st))
+                               &dv, (long long)pitch, (long long)cpitch, st, pipe ? &pa : nullptr))
         return rc;
 
-    if (out->y_final && !(zero_copy & 1u))
+    if (pipe) {
+        /* ---- upload behind the running kernel: chunk data, then the chunk's ready word (same stream: in order) */
+        const int64_t ch = (int64_t)1 << shift;
+        for (int64_t k = 0; k < n_chunks; ++k) {
+            const int64_t first = k << shift, cnt = std::min(ch, n - first);
+            CUDA_TRY(cudaMemcpy2DAsync((double*)c->y0.p + first, n * 8, y0 + lo + first, n_total * 8, cnt * 8, d,
+                                       cudaMemcpyHostToDevice, c->up_stream));
+            if (np && per_traj)
+                CUDA_TRY(cudaMemcpy2DAsync((double*)c->params.p + first, n * 8, params + lo + first, n_total * 8, cnt * 8,
+                                           np, cudaMemcpyHostToDevice, c->up_stream));
+            CUDA_TRY(cudaMemcpyAsync((unsigned*)c->pipe_dev.p + k, c->pipe_flags_host + kPipeMaxChunks, sizeof(unsigned),
+                                     cudaMemcpyHostToDevice, c->up_stream));
+        }
+        /* ---- drain: copy a chunk's per-trajectory results back as soon as the kernel has flagged it */
+        auto drain = [&](int64_t k) -> int {
+            const int64_t first = k << shift, cnt = std::min(ch, n - first);
+            cudaStream_t cs = c->copy_stream;
+            if (out->y_final)
+                CUDA_TRY(cudaMemcpy2DAsync(out->y_final + lo + first, n_total * 8, dv.y_final + first, n * 8, cnt * 8, d,
+                                           cudaMemcpyDeviceToHost, cs));
+#define DRAIN(field, elem_bytes)                                                                               \
+    if (out->field)                                                                                            \
+        CUDA_TRY(cudaMemcpyAsync((char*)out->field + (size_t)(lo + first) * (elem_bytes),                      \
+                                 (const char*)dv.field + (size_t)first * (elem_bytes), (size_t)cnt * (elem_bytes), \
+                                 cudaMemcpyDeviceToHost, cs));
+            DRAIN(x_final, 8)
+            DRAIN(h_next, 8)
+            DRAIN(num_eval, 4)
+            DRAIN(accepted, 4)
+            DRAIN(rejected, 4)
+            DRAIN(n_step, 4)
+            DRAIN(status, 4)
+            DRAIN(out_count, 4)
+            DRAIN(com_count, 4)
+            DRAIN(com_lower, 8)
+#undef DRAIN
+            return 0;
+        };
+        volatile unsigned* flags = c->pipe_flags_host;
+        int64_t next = 0;
+        unsigned spins = 0;
+        while (next < n_chunks) {
+            if (flags[next] != 0u) {
+                if (int rc = drain(next)) return rc;
+                ++next;
+                continue;
+            }
+            if ((++spins & 1023u) == 0u) {
+                const cudaError_t q = cudaStreamQuery(st);
+                if (q == cudaSuccess) { /* the kernel is done: whatever is left is complete */
+                    for (; next < n_chunks; ++next)
+                        if (int rc = drain(next)) return rc;
+                    break;
+                }
+                if (q != cudaErrorNotReady) return fail(ODE_B200_ERR_CUDA, std::string("step-loop kernel: ") + cudaGetErrorString(q));
+            }
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+        CUDA_TRY(cudaStreamSynchronize(c->up_stream));
+    }
+
+    if (out->y_final && !(zero_copy & 1u) && !pipe)
         CUDA_TRY(cudaMemcpy2DAsync(out->y_final + lo, n_total * 8, dv.y_final, n * 8, n * 8, d,
                                    cudaMemcpyDeviceToHost, st));
 #define BACK(field, elem_bytes, per)                                                                      \
@@ -628,6 +769,7 @@ static int integrate_range_impl(ode_b200_ctx* c, int sys_id, const ode_b200_conf
             BACK(field, elem_bytes, 1)             \
         }                                          \
     }
+    if (!pipe) {
     BACK_PT(x_final, 8)
     BACK_PT(h_next, 8)
     BACK_PT(num_eval, 4)
@@ -638,6 +780,7 @@ static int integrate_range_impl(ode_b200_ctx* c, int sys_id, const ode_b200_conf
     BACK_PT(out_count, 4)
     BACK_PT(com_count, 4)
     BACK_PT(com_lower, 8)
+    }
 #undef BACK_PT
     if (out->out_cap > 0) {
         const size_t cap = (size_t)out->out_cap;
@@ -668,6 +811,7 @@ static int integrate_range_impl(ode_b200_ctx* c, int sys_id, const ode_b200_conf
     }
 #undef BACK
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (pipe) CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
     return ODE_B200_SUCCESS;
 }
 

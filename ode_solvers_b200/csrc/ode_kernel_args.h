@@ -92,6 +92,17 @@ struct KernelArgs {
     long long com_pitch;        /* intervals per trajectory row of com_break / com_step / com_coef (>= out.com_cap) */
     long long out_pitch;        /* samples per trajectory row of out_x / out_y in device memory (>= out.out_cap;
                                    the host-buffer entry pads its rows to a multiple of 4) */
+    /* Host pipeline of the host-buffer entry (NULL = off, e.g. for the device-pointer entry). The batch is cut
+     * into chunks of 1 << chunk_shift consecutive trajectories. Upload: the kernel is launched BEFORE its
+     * inputs have arrived; a lane that claims a trajectory waits until upload_ready[chunk] is set (a 4-byte
+     * copy queued behind the chunk's data on the upload stream). Drain: a lane that has stored its part of a
+     * finished trajectory counts it in chunk_done[chunk]; the lane that completes a chunk raises chunk_flag
+     * [chunk] in mapped host memory, and the host, which polls the flags, copies that chunk's results back
+     * while the rest of the batch is still being integrated. */
+    int chunk_shift;
+    const unsigned* upload_ready;
+    unsigned* chunk_done;
+    unsigned* chunk_flag;
 };
 
 /* the f32 kernels' arguments (device pointers) */

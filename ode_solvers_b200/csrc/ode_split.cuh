@@ -206,7 +206,9 @@ struct Dop853SplitStepper {
 
     /* ---- result stores (per lane; the three lanes of a group always come here together) */
     ODE_DEV static double* slot_(const Lane3& L) {
-        return s_stage + ((threadIdx.x >> 5) * kSlotsPerWarp + L.base / 3u) * kSlotDoubles;
+        double* b = s_stage + ((threadIdx.x >> 5) * kSlotsPerWarp + L.base / 3u) * kSlotDoubles;
+        chk_smem_(b, kSlotDoubles);
+        return b;
     }
     /* the slot's previous bulk copies have been read by the TMA engine (the leader issued them, so it waits),
      * and the other two lanes learn it at the group barrier */
@@ -234,6 +236,7 @@ struct Dop853SplitStepper {
                 for (int c = 0; c < N; ++c) b[SS::gcomp(L.role, c)] = y[c];
                 slot_release_(L);
                 if (L.role == 0u) {
+                    chk_row_((long long)s.c.out_count, 1, a.out_pitch);
                     bulk_(a.out.out_y + q * NF, b, NF * 8);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
@@ -317,6 +320,7 @@ struct Dop853SplitStepper {
             /* the slot goes to the next trajectory only after the TMA engine has read it */
             if constexpr (STAGE) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
+        signal_done_<SS::G>(a, t);
     }
 
     /* compute_y_out, dop853.rs:546-559 */
@@ -403,11 +407,12 @@ struct Dop853SplitStepper {
     ODE_DEV static void init_all(State& s, const KernelArgs& a, long long t, bool ok, const Lane3& L) {
         const long long tt = ok ? t : 0; /* lanes that commit nothing still load from a valid row */
         double y[N], pl[2], k0[N];
+        if (ok) wait_upload_(a, tt); /* (lanes that commit nothing may read a row that has not arrived yet) */
 #pragma unroll
-        for (int c = 0; c < N; ++c) y[c] = __ldg(a.y0 + (size_t)SS::gcomp(L.role, c) * a.n_traj + tt);
+        for (int c = 0; c < N; ++c) y[c] = __ldcg(a.y0 + (size_t)SS::gcomp(L.role, c) * a.n_traj + tt);
         const int ia = SS::par_a(L.role), ib = SS::par_b(L.role);
-        pl[0] = a.params_per_traj ? __ldg(a.params + (size_t)ia * a.n_traj + tt) : __ldg(a.params + ia);
-        pl[1] = a.params_per_traj ? __ldg(a.params + (size_t)ib * a.n_traj + tt) : __ldg(a.params + ib);
+        pl[0] = a.params_per_traj ? __ldcg(a.params + (size_t)ia * a.n_traj + tt) : __ldg(a.params + ia);
+        pl[1] = a.params_per_traj ? __ldcg(a.params + (size_t)ib * a.n_traj + tt) : __ldg(a.params + ib);
         const double x = a.cfg.x0;
         double h = a.cfg.h0;
         unsigned num_eval = 0;
@@ -828,6 +833,8 @@ struct Dop853SplitStepper {
                     slot_release_(L);
                     if (L.role == 0u) {
                         if (rec_y) o.out_x[qy] = s.x;
+                        chk_row_((long long)s.c.out_count, rec_y ? 1 : 0, a.out_pitch);
+                        chk_row_((long long)s.c.com_count, rec_c ? 1 : 0, a.com_pitch);
                         if (rec_c) {
                             o.com_break[qc] = fabs(s.x);
                             o.com_step[qc] = s.h_old;

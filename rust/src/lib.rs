@@ -214,6 +214,11 @@ impl Context {
     pub fn set_work_queue(&self, enabled: bool) {
         unsafe { ffi::ode_b200_set_work_queue(self.0, enabled as std::os::raw::c_int) };
     }
+    /// Host-buffer entry: chunked upload / integrate / copy-back pipeline; `chunk_log2` = 16 by default, 0 = off
+    /// (`ode_b200_set_pipeline`).
+    pub fn set_pipeline(&self, chunk_log2: i32) {
+        unsafe { ffi::ode_b200_set_pipeline(self.0, chunk_log2) };
+    }
     /// Large states: three lanes per trajectory (default) or one thread (`ode_b200_set_lane_split`).
     pub fn set_lane_split(&self, enabled: bool) {
         unsafe { ffi::ode_b200_set_lane_split(self.0, enabled as std::os::raw::c_int) };
