@@ -320,7 +320,6 @@ struct Dop853SplitStepper {
             /* the slot goes to the next trajectory only after the TMA engine has read it */
             if constexpr (STAGE) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
-        signal_done_<SS::G>(a, t);
     }
 
     /* compute_y_out, dop853.rs:546-559 */
@@ -880,6 +879,7 @@ ODE_DEV void run_lanes_split_(const KernelArgs& a) {
     counters_init_<false>(st.c);
     st.iasti = st.non_stiff = st.stiff_ctr = 0;
     bool active = false, exhausted = !L.valid, first = true, refilled = false;
+    long long finished = -1; /* see run_lanes_ */
     int idle_acc = 0, idle_prev = 0;
     unsigned pass = 0;
     constexpr int kRefillRamp = ODE_B200_REFILL_RAMP;
@@ -890,12 +890,19 @@ ODE_DEV void run_lanes_split_(const KernelArgs& a) {
     for (;;) {
         if (pass % sync_every == 0) {
             const int n_active = __syncthreads_count(active);
-            if (n_active == 0 && refilled) break;
+            if (n_active == 0 && __syncthreads_or(!exhausted) == 0) { /* see run_lanes_ */
+                if (finished >= 0) signal_done_<3>(a, finished);
+                break;
+            }
             const int idle = group - n_active;
             idle_acc += idle * (int)sync_every;
             refilled = n_active == 0 || (idle_acc >= Stepper::kRefillIdle && kRefillRamp * (idle - idle_prev) <= idle);
             idle_prev = refilled ? 0 : idle;
             if (refilled) idle_acc = 0;
+            if (refilled && finished >= 0) {
+                signal_done_<3>(a, finished);
+                finished = -1;
+            }
             const bool want = refilled && !active && !exhausted;
             const unsigned need = idle == 0 ? 0u : __ballot_sync(kFullMask, want);
             if (need) {
@@ -919,7 +926,11 @@ ODE_DEV void run_lanes_split_(const KernelArgs& a) {
             }
             if (refilled) __syncthreads();
         }
-        if (__any_sync(kFullMask, active)) Stepper::attempt_all(st, a, active, L);
+        if (__any_sync(kFullMask, active)) {
+            const bool was = active;
+            Stepper::attempt_all(st, a, active, L);
+            if (was && !active) finished = st.traj;
+        }
         ++pass;
     }
 }

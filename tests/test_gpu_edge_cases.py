@@ -208,3 +208,25 @@ def test_two_launches_of_one_context_in_flight_on_different_streams():
                                                runs[0][5].data_ptr(), 0, None, None) == -1
     assert lib.ode_b200_integrate_batch_device(ctx.handle, f.sys_id, None, n, runs[0][4].data_ptr(),
                                                runs[0][5].data_ptr(), 0, C.byref(runs[0][6]), None) == -1
+
+
+@pytest.mark.parametrize("system", ["lorenz", "kepler", "threebody18"])
+def test_trajectories_that_end_in_the_pass_they_were_claimed_in(system):
+    """More trajectories than resident lanes, each of which finishes at its first attempt (zero Rk4 steps;
+    Dop853 with n_max = 0 -> MaxNumStepReached at once): every lane is idle right after a refill while the
+    queue still holds work. (Round 2 found the scheduler's exit test `nobody active after a refill` wrong
+    for exactly this case; it is now `nobody active and every lane has had a claim refused`.)"""
+    n = 400000 if system != "threebody18" else 60000
+    gen = {"lorenz": W.lorenz_ensemble, "kepler": W.kepler_sweep, "threebody18": W.threebody18_ensemble}[system]
+    y0, p = gen(n, offset=5)
+    f = ob.System.builtin(system)
+    for cfg, want in ((ob.config_rk4(1.0, 1.0, 0.1), ob.OK),
+                      (ob.config_from_param(ob.DOP853, 0.0, 1.0, 0.1, 1e-6, 1e-6, 0.9, 0.0, 0.333, 6.0, 1.0, 1e-3, 0, 1000,
+                                            ob.OUT_SPARSE), ob.MAX_NUM_STEP_REACHED)):
+        for queue in (True, False):
+            ctx = ob.Context(0)
+            ctx.set_work_queue(queue)
+            g = ob.integrate_batch(f, cfg, y0, p, ctx=ctx)
+            ctx.close()
+            assert (g.status == want).all(), "%d trajectories were never integrated" % int((g.status == -1).sum())
+            assert (g.y_final == y0).all() and (g.accepted == 0).all()

