@@ -302,8 +302,9 @@ int ode_b200_set_work_queue(ode_b200_ctx* ctx, int enabled);
 /* host-buffer entry: pipeline of upload, integration and copy-back. chunk_log2 = 16 (default): the batch is
  * cut into chunks of 2^16 trajectories; the kernel starts before its inputs have arrived (lanes wait for
  * their chunk), and the per-trajectory results of a finished chunk are copied back while the rest of the
- * batch is still being integrated. Used when the batch has at least two chunks and the caller's
- * per-trajectory result arrays are pinned host memory (cudaHostAlloc / cudaHostRegister); 0 switches it off
+ * batch is still being integrated. Used for built-in systems when the call asks for per-trajectory results
+ * only (out_cap = com_cap = 0), the batch has at least two chunks and the caller's result arrays are
+ * pinned host memory (cudaHostAlloc / cudaHostRegister); 0 switches it off
  * (upload, kernel, copy-back one after the other, or zero-copy result stores: ode_b200_set_zero_copy). */
 int ode_b200_set_pipeline(ode_b200_ctx* ctx, int chunk_log2);
 /* large states: 1 (default) = Dop853 runs one trajectory per group of three lanes for the systems that

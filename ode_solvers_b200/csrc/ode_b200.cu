@@ -490,6 +490,11 @@ static int launch_device(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg
     if (stream == c->stream) CUDA_TRY(cudaEventRecord(c->ev0, stream));
     if (!s.jit) {
         const void* fn = split_fn ? split_fn : kBuiltins[sys_id]->kernels[stage ? 1 : 0][cfg->method][cfg->out_type];
+        if (ka.chunk_shift > 0) { /* host pipeline: the instantiation with its device side (never staged: see integrate_range) */
+            if (stage || dyn_smem != 0) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "internal: pipelined launch of a staged kernel");
+            fn = split_fn ? kBuiltins[sys_id]->dop853_split_pipe_kernels[cfg->out_type]
+                          : kBuiltins[sys_id]->pipe_kernels[cfg->method][cfg->out_type];
+        }
         if (dyn_smem > 32 * 1024) /* static tables + dynamic rings may exceed the 48 KB default together */
             CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
         int per_sm = 0;
@@ -580,8 +585,10 @@ static int integrate_range_impl(ode_b200_ctx* c, int sys_id, const ode_b200_conf
      * zero-copy result stores / pipeline): see DESIGN.md section 5. */
     const int shift = c->pipeline_shift;
     const int64_t n_chunks = shift > 0 ? (n + ((int64_t)1 << shift) - 1) >> shift : 0;
-    bool pipe = shift > 0 && n_chunks >= 2 && n_chunks <= kPipeMaxChunks &&
-                !(cfg->method != ODE_B200_RK4 && cfg->n_stiff == 0);
+    /* ... for calls that return per-trajectory results only (the per-step arrays are copied after the kernel and
+     * dominate such a call anyway) of built-in systems (the PIPE instantiations are compiled ahead of time) */
+    bool pipe = shift > 0 && n_chunks >= 2 && n_chunks <= kPipeMaxChunks && !s.jit && out->out_cap == 0 &&
+                out->com_cap == 0 && !(cfg->method != ODE_B200_RK4 && cfg->n_stiff == 0);
     if (pipe) {
         const void* ptrs[] = {out->y_final, out->x_final, out->h_next,    out->num_eval,  out->accepted, out->rejected,
                               out->n_step,  out->status,  out->out_count, out->com_count, out->com_lower};

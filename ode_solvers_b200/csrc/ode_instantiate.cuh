@@ -38,15 +38,30 @@ const void* f32_kernel_ptr() {
       ODE_B200_KPTR(ode_b200::Dop853Stepper<ode_b200::SYS, ODE_B200_OUT_SPARSE, ST>),                        \
       ODE_B200_KPTR(ode_b200::Dop853Stepper<ode_b200::SYS, ODE_B200_OUT_CONTINUOUS8, ST>)}}
 
+#define ODE_B200_PKPTR(...) ((const void*)&ode_b200::ode_step_loop_kernel<__VA_ARGS__, true>)
+#define ODE_B200_PIPE_KSET(SYS)                                                                              \
+    {{ODE_B200_PKPTR(ode_b200::Rk4Stepper<ode_b200::SYS, false>), ODE_B200_PKPTR(ode_b200::Rk4Stepper<ode_b200::SYS, false>), \
+      ODE_B200_PKPTR(ode_b200::Rk4Stepper<ode_b200::SYS, false>), ODE_B200_PKPTR(ode_b200::Rk4Stepper<ode_b200::SYS, false>)}, \
+     {ODE_B200_PKPTR(ode_b200::Dopri5Stepper<ode_b200::SYS, ODE_B200_OUT_DENSE, false>),                      \
+      ODE_B200_PKPTR(ode_b200::Dopri5Stepper<ode_b200::SYS, ODE_B200_OUT_SPARSE, false>),                     \
+      ODE_B200_PKPTR(ode_b200::Dopri5Stepper<ode_b200::SYS, ODE_B200_OUT_CONTINUOUS, false>), nullptr},       \
+     {ODE_B200_PKPTR(ode_b200::Dop853Stepper<ode_b200::SYS, ODE_B200_OUT_DENSE, false>),                      \
+      ODE_B200_PKPTR(ode_b200::Dop853Stepper<ode_b200::SYS, ODE_B200_OUT_SPARSE, false>),                     \
+      ODE_B200_PKPTR(ode_b200::Dop853Stepper<ode_b200::SYS, ODE_B200_OUT_SPARSE, false>),                     \
+      ODE_B200_PKPTR(ode_b200::Dop853Stepper<ode_b200::SYS, ODE_B200_OUT_CONTINUOUS8, false>)}}
+
 #define ODE_B200_DEFINE_SYSTEM(SYS, NAME)                                                \
     extern "C" const ode_b200::SystemEntry ode_b200_entry_##NAME = {                     \
         #NAME, ode_b200::SYS::DIM, ode_b200::SYS::NP, ode_b200::SYS::HAS_SOLOUT ? 1 : 0, \
-        {ODE_B200_KSET(SYS, false), ODE_B200_KSET(SYS, true)}, ODE_B200_F32_KSET(SYS), \
-        {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}}, {0, 0, 0, 0}, 0, 0};
+        {ODE_B200_KSET(SYS, false), ODE_B200_KSET(SYS, true)}, ODE_B200_PIPE_KSET(SYS), ODE_B200_F32_KSET(SYS), \
+        {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}}, {0, 0, 0, 0}, 0, 0,      \
+        {nullptr, nullptr, nullptr, nullptr}};
 
 /* a system that also has a three-lanes-per-trajectory form (ode_split.cuh) for Dop853 */
 #define ODE_B200_SPLIT_KPTR(SPLIT, OUT, ST) \
     ((const void*)&ode_b200::ode_split_step_loop_kernel<ode_b200::Dop853SplitStepper<ode_b200::SPLIT, OUT, ST>>)
+#define ODE_B200_SPLIT_PKPTR(SPLIT, OUT) \
+    ((const void*)&ode_b200::ode_split_step_loop_kernel<ode_b200::Dop853SplitStepper<ode_b200::SPLIT, OUT, false>, true>)
 #define ODE_B200_SPLIT_THREADS(SPLIT, OUT) ode_b200::Dop853SplitStepper<ode_b200::SPLIT, OUT>::kThreads
 #define ODE_B200_SPLIT_KSET(SPLIT, ST)                                                                      \
     {ODE_B200_SPLIT_KPTR(SPLIT, ODE_B200_OUT_DENSE, ST), ODE_B200_SPLIT_KPTR(SPLIT, ODE_B200_OUT_SPARSE, ST), \
@@ -54,8 +69,10 @@ const void* f32_kernel_ptr() {
 #define ODE_B200_DEFINE_SYSTEM_WITH_SPLIT(SYS, NAME, SPLIT)                                                   \
     extern "C" const ode_b200::SystemEntry ode_b200_entry_##NAME = {                                          \
         #NAME, ode_b200::SYS::DIM, ode_b200::SYS::NP, ode_b200::SYS::HAS_SOLOUT ? 1 : 0,                      \
-        {ODE_B200_KSET(SYS, false), ODE_B200_KSET(SYS, true)}, ODE_B200_F32_KSET(SYS), \
+        {ODE_B200_KSET(SYS, false), ODE_B200_KSET(SYS, true)}, ODE_B200_PIPE_KSET(SYS), ODE_B200_F32_KSET(SYS), \
         {ODE_B200_SPLIT_KSET(SPLIT, false), ODE_B200_SPLIT_KSET(SPLIT, true)},                                \
         {ODE_B200_SPLIT_THREADS(SPLIT, ODE_B200_OUT_DENSE), ODE_B200_SPLIT_THREADS(SPLIT, ODE_B200_OUT_SPARSE), \
          ODE_B200_SPLIT_THREADS(SPLIT, ODE_B200_OUT_SPARSE), ODE_B200_SPLIT_THREADS(SPLIT, ODE_B200_OUT_CONTINUOUS8)}, \
-        10, ode_b200::Dop853SplitStepper<ode_b200::SPLIT, ODE_B200_OUT_SPARSE>::kSlotDoubles * 8};
+        10, ode_b200::Dop853SplitStepper<ode_b200::SPLIT, ODE_B200_OUT_SPARSE>::kSlotDoubles * 8,             \
+        {ODE_B200_SPLIT_PKPTR(SPLIT, ODE_B200_OUT_DENSE), ODE_B200_SPLIT_PKPTR(SPLIT, ODE_B200_OUT_SPARSE),   \
+         ODE_B200_SPLIT_PKPTR(SPLIT, ODE_B200_OUT_SPARSE), ODE_B200_SPLIT_PKPTR(SPLIT, ODE_B200_OUT_CONTINUOUS8)}};

@@ -909,9 +909,10 @@ struct Dop853Stepper {
 };
 
 /* ============================================================================ kernels */
-template <class Stepper>
+/* PIPE: the instantiation the host pipeline launches (ode_kernel_args.h; hooks in run_lanes_) */
+template <class Stepper, bool PIPE = false>
 __global__ void __launch_bounds__(Stepper::kThreads, Stepper::kMinBlocks) ode_step_loop_kernel(const __grid_constant__ KernelArgs a) {
-    run_lanes_<Stepper>(a);
+    run_lanes_<Stepper, KernelArgs, PIPE>(a);
 }
 
 }  // namespace ode_b200

@@ -13,6 +13,8 @@ struct SystemEntry {
     int has_solout;
     /* [staged results: no, yes][method: Rk4, Dopri5, Dop853][out_type: Dense, Sparse, Continuous, Continuous8] */
     const void* kernels[2][3][4];
+    /* the unstaged kernels once more with the host pipeline's device side compiled in (ode_kernel_args.h) */
+    const void* pipe_kernels[3][4];
     /* the steppers with T = f32 by method (nullptr when the system's RHS is f64-only) */
     const void* f32_kernels[3];
     /* Dop853 with one trajectory per group of three lanes (ode_split.cuh), by out_type; nullptr: the
@@ -21,6 +23,7 @@ struct SystemEntry {
     int split_threads[4];         /* CTA size of each of them */
     int split_traj_per_warp;      /* 10: lanes 30 and 31 stay idle */
     int split_slot_bytes;         /* shared memory per trajectory slot of a staged launch */
+    const void* dop853_split_pipe_kernels[4]; /* unstaged, with the host pipeline's device side */
 };
 
 }  // namespace ode_b200

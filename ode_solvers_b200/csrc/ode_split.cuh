@@ -406,7 +406,6 @@ struct Dop853SplitStepper {
     ODE_DEV static void init_all(State& s, const KernelArgs& a, long long t, bool ok, const Lane3& L) {
         const long long tt = ok ? t : 0; /* lanes that commit nothing still load from a valid row */
         double y[N], pl[2], k0[N];
-        if (ok) wait_upload_(a, tt); /* (lanes that commit nothing may read a row that has not arrived yet) */
 #pragma unroll
         for (int c = 0; c < N; ++c) y[c] = __ldcg(a.y0 + (size_t)SS::gcomp(L.role, c) * a.n_traj + tt);
         const int ia = SS::par_a(L.role), ib = SS::par_b(L.role);
@@ -863,13 +862,13 @@ struct Dop853SplitStepper {
 
 /* ---- lane scheduler of the split steppers: run_lanes_ (ode_device.cuh) with groups of three lanes
  * claiming one trajectory, and every shuffle-bearing phase executed by whole warps */
-template <class Stepper>
+template <class Stepper, bool PIPE = false>
 ODE_DEV void run_lanes_split_(const KernelArgs& a) {
     stage_tables_();
     Lane3 L;
     L.init();
     typename Stepper::State st;
-    st.traj = 0;
+    st.traj = -1;
     st.c.out_count = 0;
     st.x = st.h = st.x_old = st.h_old = st.xd = 0.0;
     st.pl[0] = st.pl[1] = 1.0;
@@ -879,7 +878,6 @@ ODE_DEV void run_lanes_split_(const KernelArgs& a) {
     counters_init_<false>(st.c);
     st.iasti = st.non_stiff = st.stiff_ctr = 0;
     bool active = false, exhausted = !L.valid, first = true, refilled = false;
-    long long finished = -1; /* see run_lanes_ */
     int idle_acc = 0, idle_prev = 0;
     unsigned pass = 0;
     constexpr int kRefillRamp = ODE_B200_REFILL_RAMP;
@@ -890,21 +888,15 @@ ODE_DEV void run_lanes_split_(const KernelArgs& a) {
     for (;;) {
         if (pass % sync_every == 0) {
             const int n_active = __syncthreads_count(active);
-            if (n_active == 0 && __syncthreads_or(!exhausted) == 0) { /* see run_lanes_ */
-                if (finished >= 0) signal_done_<3>(a, finished);
-                break;
-            }
+            if (n_active == 0 && refilled) break; /* the last refill handed out nothing (see run_lanes_) */
             const int idle = group - n_active;
             idle_acc += idle * (int)sync_every;
             refilled = n_active == 0 || (idle_acc >= Stepper::kRefillIdle && kRefillRamp * (idle - idle_prev) <= idle);
             idle_prev = refilled ? 0 : idle;
             if (refilled) idle_acc = 0;
-            if (refilled && finished >= 0) {
-                signal_done_<3>(a, finished);
-                finished = -1;
-            }
             const bool want = refilled && !active && !exhausted;
             const unsigned need = idle == 0 ? 0u : __ballot_sync(kFullMask, want);
+            bool claimed = false;
             if (need) {
                 const unsigned need0 = need & kLeaders;
                 long long idx;
@@ -920,24 +912,27 @@ ODE_DEV void run_lanes_split_(const KernelArgs& a) {
                 }
                 const bool ok = want && idx < a.n_traj;
                 if (want && !ok) exhausted = true;
+                if constexpr (PIPE) { /* host pipeline: report the trajectory stored last, wait for the next one's inputs */
+                    if (want && st.traj >= 0) {
+                        signal_done_<3>(a, st.traj);
+                        st.traj = -1;
+                    }
+                    if (ok) wait_upload_(a, idx);
+                }
                 Stepper::init_all(st, a, idx, ok, L);
-                if (ok) active = true;
+                if (ok) active = claimed = true;
                 first = false;
             }
-            if (refilled) __syncthreads();
+            if (refilled && __syncthreads_or(claimed)) refilled = false; /* see run_lanes_ */
         }
-        if (__any_sync(kFullMask, active)) {
-            const bool was = active;
-            Stepper::attempt_all(st, a, active, L);
-            if (was && !active) finished = st.traj;
-        }
+        if (__any_sync(kFullMask, active)) Stepper::attempt_all(st, a, active, L);
         ++pass;
     }
 }
 
-template <class Stepper>
+template <class Stepper, bool PIPE = false>
 __global__ void __launch_bounds__(Stepper::kThreads, 1) ode_split_step_loop_kernel(const __grid_constant__ KernelArgs a) {
-    run_lanes_split_<Stepper>(a);
+    run_lanes_split_<Stepper, PIPE>(a);
 }
 
 }  // namespace ode_b200
