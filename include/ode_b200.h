@@ -327,6 +327,14 @@ int ode_b200_com_evaluate(ode_b200_ctx* ctx, int64_t n_traj, int dim, int m, int
                           const double* com_lower, const double* com_break, const double* com_step,
                           const double* com_coef, const uint32_t* com_count,
                           int64_t n_query, const double* xq, double* y, uint8_t* found);
+/* The same with DEVICE pointers throughout (the model where ode_b200_integrate_batch_device left it, xq, y and
+ * found on the context's GPU), enqueued on `cuda_stream` without synchronising: resampling an ensemble on a
+ * common grid without the model ever leaving HBM. Timed by ode_b200_last_kernel_ms when cuda_stream is the
+ * context's own stream. */
+int ode_b200_com_evaluate_device(ode_b200_ctx* ctx, int64_t n_traj, int dim, int m, int64_t com_cap,
+                                 const double* com_lower, const double* com_break, const double* com_step,
+                                 const double* com_coef, const uint32_t* com_count,
+                                 int64_t n_query, const double* xq, double* y, uint8_t* found, void* cuda_stream);
 
 /* ---- introspection used by the parity tests -------------------------------------- */
 /* the device library's own copy of a tableau coefficient (0-based); which: "a5","c5","d5","e5",

@@ -183,7 +183,7 @@ ABI_SYMBOLS = [
     "ode_b200_integrate_batch", "ode_b200_integrate_batch_device", "ode_b200_integrate_batch_multi",
     "ode_b200_rk4_f32_integrate_batch", "ode_b200_integrate_batch_f32",
     "ode_b200_config_new_f32", "ode_b200_config_from_param_f32", "ode_b200_config_rk4_f32",
-    "ode_b200_set_work_queue", "ode_b200_com_evaluate",
+    "ode_b200_set_work_queue", "ode_b200_com_evaluate", "ode_b200_com_evaluate_device",
     "ode_b200_tableau", "ode_b200_debug_pow", "ode_b200_debug_exp", "ode_b200_debug_div", "ode_b200_debug_powf",
 ]
 
@@ -282,6 +282,10 @@ def load():
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ode_b200_com_evaluate.restype = C.c_int
+    lib.ode_b200_com_evaluate_device.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int64,
+                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                 C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ode_b200_com_evaluate_device.restype = C.c_int
     lib.ode_b200_tableau.argtypes = [C.c_char_p, C.c_int, C.c_int]
     lib.ode_b200_tableau.restype = C.c_double
     lib.ode_b200_debug_pow.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -1145,58 +1145,143 @@ extern "C" int ode_b200_measure_fp64_peak(int device, double* inst_per_s, double
 }
 
 /* ------------------------------------------------------------------ COM::evaluate */
-/* continuous_output_model.rs:31-56 (evaluate) and :86-104 (get_interval_index); one thread
- * per (trajectory, query). m and dim are runtime here: this kernel is HBM/latency bound. */
-__global__ void com_evaluate_kernel(long long n, int dim, int m, long long cap, const double* lower,
-                                    const double* brk, const double* stp, const double* coef,
-                                    const unsigned* count, long long nq, const double* xq, double* y,
-                                    unsigned char* found) {
-    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n * nq) return;
-    const long long t = g / nq, qi = g % nq;
-    const double x = xq[qi];
-    const unsigned cnt = (unsigned)min((long long)count[t], cap);
-    const double* bp = brk + (size_t)t * cap;
-    unsigned char ok = 0;
-    if (!(x < lower[t]) && m > 0) {
-        unsigned lo = 0, hi = cnt;
-        long long hit = -1;
-        while (lo < hi) {
-            const unsigned mid = lo + (hi - lo) / 2;
-            const double b = bp[mid];
-            if (b == x) {
-                hit = mid;
-                break;
+/*
+ * ContinuousOutputModel::evaluate (continuous_output_model.rs:31-56) with get_interval_index (:86-104), batched:
+ * n models x nq queries. HBM-bound: per (model, query) it reads the interval's m x dim coefficients + 2 scalars and
+ * writes dim + 1/8 doubles. One WARP per model: the model's breakpoints are staged in shared memory with
+ * coalesced loads (the round-1 kernel ran one thread per (model, query) and binary-searched global memory with a
+ * stride of `cap` doubles between neighbouring threads), every lane takes the queries lane, lane + 32, ... and
+ * searches its interval there, and the 32 results of a round are written as ONE contiguous block of 32 x dim
+ * doubles. Neighbouring queries fall into the same or neighbouring intervals, so the coefficient loads of a round
+ * hit the same few cache lines. M and D are compile-time for the shapes the steppers produce (Horner fully unrolled);
+ * other shapes take the generic instantiation (M = D = 0: runtime loops).
+ * Bit parity: theta = (x - lower) / step, then r = c[m-1]; r = c[q] + r * (q even ? theta : 1 - theta), as the source.
+ */
+constexpr int kComWarps = 4;        /* warps (= models) per CTA */
+constexpr int kComStageMax = 1536;  /* breakpoints per model that fit the CTA's shared memory (4 x 12 KB) */
+
+template <int M, int D>
+__global__ void __launch_bounds__(kComWarps * 32) com_evaluate_kernel(long long n, int dim_rt, int m_rt, long long cap,
+                                                                      const double* __restrict__ lower,
+                                                                      const double* __restrict__ brk,
+                                                                      const double* __restrict__ stp,
+                                                                      const double* __restrict__ coef,
+                                                                      const unsigned* __restrict__ count, long long nq,
+                                                                      const double* __restrict__ xq, double* __restrict__ y,
+                                                                      unsigned char* __restrict__ found) {
+    __shared__ double s_brk[kComWarps][kComStageMax];
+    const int dim = D > 0 ? D : dim_rt, m = M > 0 ? M : m_rt;
+    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    for (long long t = (long long)blockIdx.x * kComWarps + w; t < n; t += (long long)gridDim.x * kComWarps) {
+        const unsigned cnt = (unsigned)min((long long)count[t], cap);
+        const double* bp = brk + (size_t)t * cap;
+        const bool staged = cnt <= (unsigned)kComStageMax;
+        __syncwarp();
+        if (staged)
+            for (unsigned i = lane; i < cnt; i += 32u) s_brk[w][i] = bp[i];
+        __syncwarp();
+        const double lb0 = lower[t];
+        for (long long q0 = 0; q0 < nq; q0 += 32) {
+            const long long qi = q0 + lane;
+            if (qi >= nq) continue;
+            const double x = xq[qi];
+            unsigned char ok = 0;
+            double* yo = y + ((size_t)t * nq + qi) * dim;
+            if (!(x < lb0) && m > 0 && x == x) { /* x < lower_bound -> None; NaN: partial_cmp().unwrap() panics */
+                /* first index with breakpoint >= x: the match of binary_search_by, or its insertion point */
+                unsigned lo = 0, hi = cnt;
+                while (lo < hi) {
+                    const unsigned mid = lo + (hi - lo) / 2;
+                    const double b = staged ? s_brk[w][mid] : __ldg(bp + mid);
+                    if (b < x)
+                        lo = mid + 1;
+                    else
+                        hi = mid;
+                }
+                if (lo < cnt) {
+                    const double lb = lo == 0 ? lb0 : (staged ? s_brk[w][lo - 1] : __ldg(bp + lo - 1));
+                    const double theta = (x - lb) / __ldg(stp + (size_t)t * cap + lo), theta1 = 1.0 - theta;
+                    const double* c = coef + ((size_t)t * cap + lo) * m * dim;
+                    if constexpr (M > 0 && D > 0) {
+                        double r[D];
+#pragma unroll
+                        for (int i = 0; i < D; ++i) r[i] = __ldg(c + (M - 1) * D + i);
+#pragma unroll
+                        for (int k = M - 2; k >= 0; --k)
+#pragma unroll
+                            for (int i = 0; i < D; ++i) r[i] = __ldg(c + k * D + i) + r[i] * ((k % 2 == 0) ? theta : theta1);
+#pragma unroll
+                        for (int i = 0; i < D; ++i) yo[i] = r[i];
+                    } else {
+                        for (int i = 0; i < dim; ++i) {
+                            double r = __ldg(c + (size_t)(m - 1) * dim + i);
+                            for (int k = m - 2; k >= 0; --k)
+                                r = __ldg(c + (size_t)k * dim + i) + r * ((k % 2 == 0) ? theta : theta1);
+                            yo[i] = r;
+                        }
+                    }
+                    ok = 1;
+                }
             }
-            if (b < x)
-                lo = mid + 1;
-            else
-                hi = mid;
-        }
-        long long index = hit >= 0 ? hit : (lo < cnt ? (long long)lo : -1);
-        if (index >= 0) {
-            const double lb = index == 0 ? lower[t] : bp[index - 1];
-            const double theta = (x - lb) / stp[(size_t)t * cap + index], theta1 = 1.0 - theta;
-            const double* c = coef + ((size_t)t * cap + index) * m * dim;
-            for (int i = 0; i < dim; ++i) {
-                double r = c[(size_t)(m - 1) * dim + i];
-                for (int q = m - 2; q >= 0; --q) r = c[(size_t)q * dim + i] + r * ((q % 2 == 0) ? theta : theta1);
-                y[(size_t)g * dim + i] = r;
-            }
-            ok = 1;
+            found[(size_t)t * nq + qi] = ok;
         }
     }
-    found[g] = ok;
+}
+
+typedef void (*com_kernel_t)(long long, int, int, long long, const double*, const double*, const double*, const double*,
+                             const unsigned*, long long, const double*, double*, unsigned char*);
+static com_kernel_t com_kernel_for(int m, int dim) {
+#define COM_CASE(MM, DD) \
+    if (m == MM && dim == DD) return com_evaluate_kernel<MM, DD>;
+    COM_CASE(5, 1) COM_CASE(5, 2) COM_CASE(5, 3) COM_CASE(5, 4) COM_CASE(5, 6) COM_CASE(5, 18)
+    COM_CASE(8, 1) COM_CASE(8, 2) COM_CASE(8, 3) COM_CASE(8, 6) COM_CASE(8, 18)
+#undef COM_CASE
+    return com_evaluate_kernel<0, 0>;
+}
+
+static int com_validate(ode_b200_ctx* c, int64_t n, int dim, int m, int64_t cap, const void* lower, const void* brk,
+                        const void* stp, const void* coef, const void* count, int64_t nq, const void* xq, const void* y,
+                        const void* found) {
+    if (!c) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    if (n < 0 || nq < 0 || dim < 1 || m < 0 || cap < 1 || !lower || !brk || !stp || !coef || !count || !xq || !y || !found)
+        return fail(ODE_B200_ERR_INVALID_ARGUMENT, "com_evaluate: bad arguments");
+    return 0;
+}
+
+static int com_launch(ode_b200_ctx* c, int64_t n, int dim, int m, int64_t cap, const double* lower, const double* brk,
+                      const double* stp, const double* coef, const uint32_t* count, int64_t nq, const double* xq, double* y,
+                      uint8_t* found, cudaStream_t st) {
+    const long long blocks = std::min<long long>((n + kComWarps - 1) / kComWarps, (long long)c->num_sms * 16);
+    com_kernel_for(m, dim)<<<(unsigned)blocks, kComWarps * 32, 0, st>>>(n, dim, m, cap, lower, brk, stp, coef, count, nq, xq, y,
+                                                                      found);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ODE_B200_SUCCESS;
+}
+
+/* device pointers: the model is where ode_b200_integrate_batch_device left it; enqueued on `cuda_stream`, not synchronised */
+extern "C" int ode_b200_com_evaluate_device(ode_b200_ctx* c, int64_t n, int dim, int m, int64_t cap, const double* lower,
+                                            const double* brk, const double* stp, const double* coef,
+                                            const uint32_t* count, int64_t nq, const double* xq, double* y, uint8_t* found,
+                                            void* cuda_stream) {
+    if (int rc = com_validate(c, n, dim, m, cap, lower, brk, stp, coef, count, nq, xq, y, found)) return rc;
+    if (n == 0 || nq == 0) return ODE_B200_SUCCESS;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (st == c->stream) CUDA_TRY(cudaEventRecord(c->ev0, st));
+    if (int rc = com_launch(c, n, dim, m, cap, lower, brk, stp, coef, count, nq, xq, y, found, st)) return rc;
+    if (st == c->stream) {
+        CUDA_TRY(cudaEventRecord(c->ev1, st));
+        c->timed = true;
+    }
+    return ODE_B200_SUCCESS;
 }
 
 extern "C" int ode_b200_com_evaluate(ode_b200_ctx* c, int64_t n, int dim, int m, int64_t cap,
                                      const double* lower, const double* brk, const double* stp,
                                      const double* coef, const uint32_t* count, int64_t nq, const double* xq,
                                      double* y, uint8_t* found) {
-    if (!c) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
-    if (n < 0 || nq < 0 || dim < 1 || m < 0 || cap < 1 || !lower || !brk || !stp || !coef || !count || !xq || !y ||
-        !found)
-        return fail(ODE_B200_ERR_INVALID_ARGUMENT, "com_evaluate: bad arguments");
+    if (int rc = com_validate(c, n, dim, m, cap, lower, brk, stp, coef, count, nq, xq, y, found)) return rc;
     if (n == 0 || nq == 0) return ODE_B200_SUCCESS;
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
@@ -1205,23 +1290,31 @@ extern "C" int ode_b200_com_evaluate(ode_b200_ctx* c, int64_t n, int dim, int m,
         ensure(c, c->com_coef, nc) || ensure(c, c->com_count, n * 4) || ensure(c, c->scratch0, nq * 8) ||
         ensure(c, c->scratch1, (size_t)n * nq * dim * 8) || ensure(c, c->scratch2, (size_t)n * nq))
         return ODE_B200_ERR_CUDA;
-    CUDA_TRY(cudaMemcpyAsync(c->com_lower.p, lower, n * 8, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(c->com_break.p, brk, nb, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(c->com_step.p, stp, nb, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(c->com_coef.p, coef, nc, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(c->com_count.p, count, n * 4, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(c->scratch0.p, xq, nq * 8, cudaMemcpyHostToDevice, st));
-    const long long total = (long long)n * nq;
-    com_evaluate_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-        n, dim, m, cap, (const double*)c->com_lower.p, (const double*)c->com_break.p,
-        (const double*)c->com_step.p, (const double*)c->com_coef.p, (const unsigned*)c->com_count.p, nq,
-        (const double*)c->scratch0.p, (double*)c->scratch1.p, (unsigned char*)c->scratch2.p);
-    c->launches++;
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(y, c->scratch1.p, (size_t)total * dim * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(found, c->scratch2.p, (size_t)total, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    return ODE_B200_SUCCESS;
+    int rc = ODE_B200_SUCCESS;
+    auto body = [&]() -> int {
+        CUDA_TRY(cudaMemcpyAsync(c->com_lower.p, lower, n * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(c->com_break.p, brk, nb, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(c->com_step.p, stp, nb, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(c->com_coef.p, coef, nc, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(c->com_count.p, count, n * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(c->scratch0.p, xq, nq * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaEventRecord(c->ev0, st));
+        if (int r = com_launch(c, n, dim, m, cap, (const double*)c->com_lower.p, (const double*)c->com_break.p,
+                               (const double*)c->com_step.p, (const double*)c->com_coef.p, (const uint32_t*)c->com_count.p,
+                               nq, (const double*)c->scratch0.p, (double*)c->scratch1.p, (uint8_t*)c->scratch2.p, st))
+            return r;
+        CUDA_TRY(cudaEventRecord(c->ev1, st));
+        c->timed = true;
+        CUDA_TRY(cudaMemcpyAsync(y, c->scratch1.p, (size_t)n * nq * dim * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(found, c->scratch2.p, (size_t)n * nq, cudaMemcpyDeviceToHost, st));
+        return ODE_B200_SUCCESS;
+    };
+    rc = body();
+    const std::string keep = g_last_error;
+    const cudaError_t e = cudaStreamSynchronize(st); /* also on an error path: no copy may outlive the call */
+    if (rc == ODE_B200_SUCCESS && e != cudaSuccess) return fail(ODE_B200_ERR_CUDA, cudaGetErrorString(e));
+    if (rc != ODE_B200_SUCCESS) g_last_error = keep;
+    return rc;
 }
 
 /* ------------------------------------------------------------------ introspection */

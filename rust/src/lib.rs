@@ -662,3 +662,18 @@ pub fn com_evaluate_batch(ctx: &Context, n: usize, dim: usize, m: usize, com_cap
     };
     if rc != 0 { Err(IntegrationError::Backend(last_error())) } else { Ok((y, found)) }
 }
+
+/// Device-pointer form (`ode_b200_com_evaluate_device`): the model where `integrate_batch_device` left it, `xq`, `y`
+/// and `found` on the context's GPU; enqueued on `stream` without synchronising.
+///
+/// # Safety
+/// All pointers must be valid device allocations of the documented sizes until the stream has finished.
+#[allow(clippy::too_many_arguments)]
+pub unsafe fn com_evaluate_device(ctx: &Context, n: usize, dim: usize, m: usize, com_cap: usize, com_lower: *const f64,
+                                  com_break: *const f64, com_step: *const f64, com_coef: *const f64,
+                                  com_count: *const u32, n_query: usize, xq: *const f64, y: *mut f64, found: *mut u8,
+                                  stream: *mut std::os::raw::c_void) -> Result<(), IntegrationError> {
+    let rc = ffi::ode_b200_com_evaluate_device(ctx.0, n as i64, dim as i32, m as i32, com_cap as i64, com_lower, com_break,
+                                               com_step, com_coef, com_count, n_query as i64, xq, y, found, stream);
+    if rc != 0 { Err(IntegrationError::Backend(last_error())) } else { Ok(()) }
+}

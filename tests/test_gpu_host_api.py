@@ -355,3 +355,58 @@ def test_dop853_continuous_output_model_extension():
     cfg = ob.config_new(ob.DOPRI5, 0.0, 1.0, 0.1, 1e-6, 1e-6, out_type=ob.OUT_CONTINUOUS8)
     with pytest.raises(ob.Ode200Error):
         ob.integrate_batch(f, cfg, np.asarray(W.CR3BP_Y0).reshape(6, 1))
+
+
+def test_com_evaluate_device_entry_unsorted_nan_large_capacity_and_generic_shape():
+    """ode_b200_com_evaluate / _device after the round-2 rewrite (one warp per model, breakpoints staged in shared
+    memory): unsorted queries, queries outside the bounds, NaN, a capacity beyond the staging limit (breakpoints read
+    from global memory), the (m, dim) shapes without a compile-time instantiation, and the device-pointer entry"""
+    import ctypes as C
+    import torch
+    from ode_solvers_b200 import _abi
+    lib = _abi.load()
+    rng = np.random.default_rng(3)
+    # (a) Lorenz / Dopri5, ragged interval counts, small and huge capacity
+    y0, p = W.lorenz_ensemble(150, offset=9)
+    cfg = ob.config_new(ob.DOPRI5, 0.0, 3.0, 0.1, 1e-7, 1e-7, out_type=ob.OUT_CONTINUOUS)
+    for cap in (400, 2000):
+        g = ob.integrate_batch(ob.System.builtin("lorenz"), cfg, y0, p, out_cap=cap, com_cap=cap)
+        xq = np.concatenate([rng.uniform(-0.5, 3.5, 97), [0.0, 3.0, np.nan, -0.0, 1e300], g.com_break[0, :5]])
+        y, found = ob.com_evaluate_batch(g, xq)
+        for i in range(0, g.n, 7):
+            for q, x in enumerate(xq):
+                r = oracle.com_evaluate(g, i, x) if x == x else None
+                assert (r is not None) == bool(found[i, q]), (cap, i, x)
+                if r is not None:
+                    assert same_f64(y[i, q], r).all(), (cap, i, x)
+    # (b) a 5-dimensional user system (no compile-time (5, 5) instantiation) and Dop853's 8-row intervals of dim 1
+    f5 = ob.System.from_source("decay5", 5, 1, "for (int i = 0; i < 5; ++i) dy[i] = -p[0] * (i + 1) * y[i];", params=[0.7])
+    g5 = ob.integrate_batch(f5, ob.config_new(ob.DOPRI5, 0.0, 2.0, 0.1, 1e-8, 1e-8, out_type=ob.OUT_CONTINUOUS),
+                            rng.uniform(0.5, 2.0, (5, 40)), out_cap=300, com_cap=300)
+    g1 = ob.integrate_batch(ob.System.builtin("test_exp"), ob.config_new(ob.DOP853, 0.0, 1.0, 0.1, 1e-9, 1e-9,
+                                                                        out_type=ob.OUT_CONTINUOUS8),
+                            np.linspace(0.5, 1.5, 40).reshape(1, -1), out_cap=300, com_cap=300)
+    for g in (g5, g1):
+        xq = rng.uniform(0.0, g.x_final[0], 33)
+        y, found = ob.com_evaluate_batch(g, xq)
+        assert found.all()
+        for i in range(0, g.n, 3):
+            for q, x in enumerate(xq):
+                assert same_f64(y[i, q], oracle.com_evaluate(g, i, x)).all()
+    # (c) the device-pointer entry on the model of (a)
+    dev = torch.device("cuda", 0)
+    ctx = ob.default_context(0)
+    xq = np.sort(rng.uniform(0.0, 3.0, 500))
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    g = ob.integrate_batch(ob.System.builtin("lorenz"), cfg, y0, p, out_cap=400, com_cap=400)
+    d = {k: up(getattr(g, k)) for k in ("com_lower", "com_break", "com_step", "com_coef", "com_count")}
+    d_xq, d_y = up(xq), torch.zeros((g.n, 500, 3), dtype=torch.float64, device=dev)
+    d_f = torch.zeros((g.n, 500), dtype=torch.uint8, device=dev)
+    rc = lib.ode_b200_com_evaluate_device(ctx.handle, g.n, 3, 5, 400, d["com_lower"].data_ptr(), d["com_break"].data_ptr(),
+                                          d["com_step"].data_ptr(), d["com_coef"].data_ptr(), d["com_count"].data_ptr(), 500,
+                                          d_xq.data_ptr(), d_y.data_ptr(), d_f.data_ptr(), lib.ode_b200_stream(ctx.handle))
+    assert rc == 0, _abi.last_error()
+    torch.cuda.synchronize()
+    yh, fh = ob.com_evaluate_batch(g, xq)
+    assert np.array_equal(d_f.cpu().numpy().astype(bool), fh) and same_f64(d_y.cpu().numpy()[fh], yh[fh]).all()
+    assert ctx.last_kernel_ms > 0.0
