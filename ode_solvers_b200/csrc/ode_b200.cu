@@ -1148,37 +1148,55 @@ extern "C" int ode_b200_measure_fp64_peak(int device, double* inst_per_s, double
 /*
  * ContinuousOutputModel::evaluate (continuous_output_model.rs:31-56) with get_interval_index (:86-104), batched:
  * n models x nq queries. HBM-bound: per (model, query) it reads the interval's m x dim coefficients + 2 scalars and
- * writes dim + 1/8 doubles. One WARP per model: the model's breakpoints are staged in shared memory with
- * coalesced loads (the round-1 kernel ran one thread per (model, query) and binary-searched global memory with a
- * stride of `cap` doubles between neighbouring threads), every lane takes the queries lane, lane + 32, ... and
- * searches its interval there, and the 32 results of a round are written as ONE contiguous block of 32 x dim
- * doubles. Neighbouring queries fall into the same or neighbouring intervals, so the coefficient loads of a round
+ * writes dim + 1/8 doubles. One WARP per model (the round-1 kernel ran one thread per (model, query) and
+ * binary-searched global memory with a stride of `cap` doubles between neighbouring threads): every lane takes the
+ * queries lane, lane + 32, ..., finds its interval through a coarse index of the model's breakpoints in shared
+ * memory, and the 32 results of a round are written as ONE contiguous block of 32 x dim doubles. Neighbouring queries fall into the same or neighbouring intervals, so the coefficient loads of a round
  * hit the same few cache lines. M and D are compile-time for the shapes the steppers produce (Horner fully unrolled);
  * other shapes take the generic instantiation (M = D = 0: runtime loops).
  * Bit parity: theta = (x - lower) / step, then r = c[m-1]; r = c[q] + r * (q even ? theta : 1 - theta), as the source.
  */
-constexpr int kComWarps = 4;        /* warps (= models) per CTA */
-constexpr int kComStageMax = 1536;  /* breakpoints per model that fit the CTA's shared memory (4 x 12 KB) */
+constexpr int kComWarps = 8;     /* warps (= models) per CTA */
+constexpr int kComCoarse = 192;  /* entries of a model's coarse breakpoint index in shared memory */
+
+/* first index in [lo, hi) whose breakpoint is >= x (hi if none): the match of the reference's binary_search_by
+ * (breakpoints are strictly increasing), or its insertion point */
+template <class Load>
+__device__ __forceinline__ unsigned com_lower_bound_(unsigned lo, unsigned hi, double x, Load load) {
+    while (lo < hi) {
+        const unsigned mid = lo + (hi - lo) / 2;
+        if (load(mid) < x)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
 
 template <int M, int D>
-__global__ void __launch_bounds__(kComWarps * 32) com_evaluate_kernel(long long n, int dim_rt, int m_rt, long long cap,
-                                                                      const double* __restrict__ lower,
-                                                                      const double* __restrict__ brk,
-                                                                      const double* __restrict__ stp,
-                                                                      const double* __restrict__ coef,
-                                                                      const unsigned* __restrict__ count, long long nq,
-                                                                      const double* __restrict__ xq, double* __restrict__ y,
-                                                                      unsigned char* __restrict__ found) {
-    __shared__ double s_brk[kComWarps][kComStageMax];
+__global__ void __launch_bounds__(kComWarps * 32, 6) com_evaluate_kernel(long long n, int dim_rt, int m_rt, long long cap,
+                                                                         const double* __restrict__ lower,
+                                                                         const double* __restrict__ brk,
+                                                                         const double* __restrict__ stp,
+                                                                         const double* __restrict__ coef,
+                                                                         const unsigned* __restrict__ count, long long nq,
+                                                                         const double* __restrict__ xq, double* __restrict__ y,
+                                                                         unsigned char* __restrict__ found) {
+    /* Two-level search. A full copy of the breakpoints in shared memory (the first version of this kernel: 12 KB
+     * per warp) left 16 warps per SM and the kernel latency-bound (ncu: "long scoreboard" 9.9 stalls per issue,
+     * 2.9 TB/s). Now every warp keeps a coarse index of its model -- every s-th breakpoint, s = ceil(count / 192),
+     * 1.5 KB -- which narrows a query down to s breakpoints; those are read from global memory (cached: the
+     * queries of a round are neighbours) for the last log2(s) steps. 48 warps per SM. */
+    __shared__ double s_idx[kComWarps][kComCoarse];
     const int dim = D > 0 ? D : dim_rt, m = M > 0 ? M : m_rt;
     const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     for (long long t = (long long)blockIdx.x * kComWarps + w; t < n; t += (long long)gridDim.x * kComWarps) {
         const unsigned cnt = (unsigned)min((long long)count[t], cap);
         const double* bp = brk + (size_t)t * cap;
-        const bool staged = cnt <= (unsigned)kComStageMax;
+        const unsigned s = (cnt + kComCoarse - 1) / kComCoarse;                 /* stride of the coarse index */
+        const unsigned nc = s ? (cnt + s - 1) / s : 0;                          /* its length: entry j = bp[min((j + 1) s, cnt) - 1] */
         __syncwarp();
-        if (staged)
-            for (unsigned i = lane; i < cnt; i += 32u) s_brk[w][i] = bp[i];
+        for (unsigned j = lane; j < nc; j += 32u) s_idx[w][j] = __ldg(bp + min((j + 1u) * s, cnt) - 1u);
         __syncwarp();
         const double lb0 = lower[t];
         for (long long q0 = 0; q0 < nq; q0 += 32) {
@@ -1188,18 +1206,13 @@ __global__ void __launch_bounds__(kComWarps * 32) com_evaluate_kernel(long long 
             unsigned char ok = 0;
             double* yo = y + ((size_t)t * nq + qi) * dim;
             if (!(x < lb0) && m > 0 && x == x) { /* x < lower_bound -> None; NaN: partial_cmp().unwrap() panics */
-                /* first index with breakpoint >= x: the match of binary_search_by, or its insertion point */
-                unsigned lo = 0, hi = cnt;
-                while (lo < hi) {
-                    const unsigned mid = lo + (hi - lo) / 2;
-                    const double b = staged ? s_brk[w][mid] : __ldg(bp + mid);
-                    if (b < x)
-                        lo = mid + 1;
-                    else
-                        hi = mid;
-                }
+                /* block j holds breakpoints [j s, min((j + 1) s, cnt)); its last one is s_idx[j]: the first block whose
+                 * last breakpoint is >= x contains the answer */
+                const unsigned j = com_lower_bound_(0u, nc, x, [&](unsigned k) { return s_idx[w][k]; });
+                unsigned lo = cnt;
+                if (j < nc) lo = com_lower_bound_(j * s, min((j + 1u) * s, cnt) - 1u, x, [&](unsigned k) { return __ldg(bp + k); });
                 if (lo < cnt) {
-                    const double lb = lo == 0 ? lb0 : (staged ? s_brk[w][lo - 1] : __ldg(bp + lo - 1));
+                    const double lb = lo == 0 ? lb0 : __ldg(bp + lo - 1);
                     const double theta = (x - lb) / __ldg(stp + (size_t)t * cap + lo), theta1 = 1.0 - theta;
                     const double* c = coef + ((size_t)t * cap + lo) * m * dim;
                     if constexpr (M > 0 && D > 0) {
@@ -1251,7 +1264,7 @@ static int com_validate(ode_b200_ctx* c, int64_t n, int dim, int m, int64_t cap,
 static int com_launch(ode_b200_ctx* c, int64_t n, int dim, int m, int64_t cap, const double* lower, const double* brk,
                       const double* stp, const double* coef, const uint32_t* count, int64_t nq, const double* xq, double* y,
                       uint8_t* found, cudaStream_t st) {
-    const long long blocks = std::min<long long>((n + kComWarps - 1) / kComWarps, (long long)c->num_sms * 16);
+    const long long blocks = std::min<long long>((n + kComWarps - 1) / kComWarps, (long long)c->num_sms * 6);
     com_kernel_for(m, dim)<<<(unsigned)blocks, kComWarps * 32, 0, st>>>(n, dim, m, cap, lower, brk, stp, coef, count, nq, xq, y,
                                                                       found);
     c->launches++;
