@@ -330,7 +330,8 @@ int ode_b200_com_evaluate(ode_b200_ctx* ctx, int64_t n_traj, int dim, int m, int
 /* The same with DEVICE pointers throughout (the model where ode_b200_integrate_batch_device left it, xq, y and
  * found on the context's GPU), enqueued on `cuda_stream` without synchronising: resampling an ensemble on a
  * common grid without the model ever leaving HBM. Timed by ode_b200_last_kernel_ms when cuda_stream is the
- * context's own stream. */
+ * context's own stream. Ascending queries are several times faster than unordered ones (neighbouring lanes
+ * then read neighbouring intervals); the host-pointer entry above sorts unordered queries itself. */
 int ode_b200_com_evaluate_device(ode_b200_ctx* ctx, int64_t n_traj, int dim, int m, int64_t com_cap,
                                  const double* com_lower, const double* com_break, const double* com_step,
                                  const double* com_coef, const uint32_t* com_count,
