@@ -478,7 +478,7 @@ static int launch_device(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg
         ((ka.com_pitch & 1) != 0 || ((uintptr_t)ka.out.com_break & 15u) != 0 || ((uintptr_t)ka.out.com_step & 15u) != 0 ||
          ((uintptr_t)ka.out.com_coef & 15u) != 0))
         stage = false;
-    size_t dyn_smem = stage ? (size_t)stage_smem_doubles(s.dim, block, com_m) * sizeof(double) : 0;
+    size_t dyn_smem = stage ? (size_t)stage_smem_doubles(s.dim, block, com_m, cfg->method) * sizeof(double) : 0;
     if (split_fn && ka.out.out_x != nullptr && ((uintptr_t)ka.out.out_y & 15u) == 0 &&
         (ka.out.com_break == nullptr || ((uintptr_t)ka.out.com_coef & 15u) == 0)) {
         /* the split kernels stage recorded results per trajectory slot (whole rows of the result arrays:

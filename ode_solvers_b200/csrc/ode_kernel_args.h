@@ -55,10 +55,22 @@ __host__ __device__ constexpr bool records_dense(int method, int out_type) {
  * It needs an even row pitch (alignment) and shared memory, so the launcher picks it only for
  * output-heavy calls (rule in ode_b200.cu). Lane buffer: x[R] then y[R][dim], R = 2 groups.
  */
-__host__ __device__ constexpr int stage_group(int dim) { return dim <= 4 ? 4 : 2; }
-__host__ __device__ constexpr int stage_samples(int dim) { return 2 * stage_group(dim); }
+/* Groups of 8 samples for Rk4 (a bulk copy then moves 192 B instead of 96 B; tools/micro/bulk_store.cu: 4.3-4.6 TB/s
+ * against 3.5-4.0 for the pattern alone) were measured in round 2 (-DODE_B200_RK4_GROUP=8): 528 B of ring per lane
+ * leave 3 instead of 5 CTAs per SM, and the kernel that records every Rk4 step goes 4.63 -> 4.50 ms at 2^18
+ * trajectories (3.63 -> 3.73 TB/s) but 2.51 -> 2.59 ms at 2^17: it is bound by instruction issue (ncu: 73 % of the
+ * issue slots), not by the size of its copies. Not kept. */
+#ifndef ODE_B200_RK4_GROUP
+#define ODE_B200_RK4_GROUP 4
+#endif
+__host__ __device__ constexpr int stage_group(int dim, int method = ODE_B200_DOPRI5) {
+    return dim <= 4 ? (method == ODE_B200_RK4 ? ODE_B200_RK4_GROUP : 4) : 2;
+}
+__host__ __device__ constexpr int stage_samples(int dim, int method = ODE_B200_DOPRI5) { return 2 * stage_group(dim, method); }
 /* in doubles; even (16-byte aligned lane buffers), and not a multiple of 32 (shared-memory banks) */
-__host__ __device__ constexpr int stage_stride(int dim) { return stage_samples(dim) * (1 + dim) + 2; }
+__host__ __device__ constexpr int stage_stride(int dim, int method = ODE_B200_DOPRI5) {
+    return stage_samples(dim, method) * (1 + dim) + 2;
+}
 /* ContinuousOutputModel intervals (breakpoint, step size, m coefficient vectors) are staged the same
  * way when they fit: a ring of two groups of 2 intervals per lane -- break[4], step[4], coef[4][m][dim]
  * -- each group leaving as one bulk copy (coefficients) and two 16-byte stores. 0 = written directly (large dim * m). */
@@ -67,8 +79,8 @@ __host__ __device__ constexpr int com_stage_stride(int dim, int m, int threads) 
 }
 /* dynamic shared memory of a staging launch; m = coefficient vectors per interval of the call's
  * continuous output model (0: none recorded) */
-__host__ __device__ constexpr int stage_smem_doubles(int dim, int threads, int m) {
-    return threads * (stage_stride(dim) + (m > 0 ? com_stage_stride(dim, m, threads) : 0));
+__host__ __device__ constexpr int stage_smem_doubles(int dim, int threads, int m, int method = ODE_B200_DOPRI5) {
+    return threads * (stage_stride(dim, method) + (m > 0 ? com_stage_stride(dim, m, threads) : 0));
 }
 
 struct KernelArgs {

@@ -117,7 +117,7 @@ struct Rk4Stepper {
         s.x = a.cfg.x0;
         counters_init_<STAGE>(s.c);
         s.status = ODE_B200_OK;
-        push_<N, STAGE>(a, t, s.c, s.x, s.y);
+        push_<N, STAGE, 0, ODE_B200_RK4>(a, t, s.c, s.x, s.y);
         const double ns = ceil((a.cfg.x_end - s.x) / a.cfg.step_size);
         if (!(ns >= 0.0) || ns > 4.0e9) { /* to_usize().unwrap() panics in the reference */
             s.status = ODE_B200_UNSUPPORTED_DOMAIN;
@@ -163,7 +163,7 @@ struct Rk4Stepper {
     /* one Rk4::step + the loop body of integrate, rk4.rs:79-98,103-132 */
     ODE_DEV static bool attempt(State& s, const KernelArgs& a) {
         if (s.steps_left == 0) {
-            store_final_<N, STAGE>(a, s.traj, s.y, s.x, a.cfg.step_size, s.c, s.status, 0.0);
+            store_final_<N, STAGE, 1, 0, ODE_B200_RK4>(a, s.traj, s.y, s.x, a.cfg.step_size, s.c, s.status, 0.0);
             return true;
         }
         const double step = a.cfg.step_size, x = s.x;
@@ -193,14 +193,14 @@ struct Rk4Stepper {
         s.x = x_new;
 #pragma unroll
         for (int i = 0; i < N; ++i) s.y[i] = w.yn[i];
-        push_<N, STAGE>(a, s.traj, s.c, x_new, w.yn);
+        push_<N, STAGE, 0, ODE_B200_RK4>(a, s.traj, s.c, x_new, w.yn);
         s.c.num_eval += 4;
         s.c.accepted += 1;
         s.c.n_step += 1;
         s.steps_left -= 1;
         if (stop) s.steps_left = 0;
         if (s.steps_left == 0) {
-            store_final_<N, STAGE>(a, s.traj, s.y, s.x, step, s.c, s.status, 0.0);
+            store_final_<N, STAGE, 1, 0, ODE_B200_RK4>(a, s.traj, s.y, s.x, step, s.c, s.status, 0.0);
             return true;
         }
         return false;
@@ -357,6 +357,9 @@ struct Dopri5Stepper {
             MathExact mx;
             core<MathExact>(s.y, s.k0, s.p, s.ctrl.pw_old, a, x, h, w, mx);
         }
+#ifdef ODE_B200_EXPERIMENT_NOCOLD
+        if (__builtin_expect(kSpec && m.bad(), 0)) __trap();
+#else
         if (__builtin_expect(kSpec && m.bad(), 0)) { /* some operand left the fast paths' window: redo it exactly */
             ColdIn in;
             Work w2;
@@ -373,6 +376,7 @@ struct Dopri5Stepper {
             core_exact(&in, &a, &w2);
             w = w2;
         }
+#endif
         s.c.num_eval += 6;
         double(&k)[7][N] = w.k;
         double(&ynext)[N] = w.ynext;
