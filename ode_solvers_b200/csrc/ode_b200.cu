@@ -438,10 +438,14 @@ static int launch_device(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg
         ka.chunk_flag = pipe->chunk_flag;
     }
 
-    /* large states (ode_split.cuh): Dop853 with one trajectory per group of three lanes */
+    /* large states (ode_split.cuh): Dopri5 / Dop853 with one trajectory per group of three lanes */
     const void* split_fn = nullptr;
-    if (!s.jit && cfg->method == ODE_B200_DOP853 && c->lane_split) split_fn = kBuiltins[sys_id]->dop853_split_kernels[0][cfg->out_type];
-    const int block = split_fn ? kBuiltins[sys_id]->split_threads[cfg->out_type]
+    const SystemEntry::SplitKernels* split = nullptr;
+    if (!s.jit && cfg->method != ODE_B200_RK4 && c->lane_split) {
+        split = &kBuiltins[sys_id]->split[cfg->method == ODE_B200_DOP853 ? 1 : 0];
+        split_fn = split->fn[0][cfg->out_type];
+    }
+    const int block = split_fn ? split->threads[cfg->out_type]
                                : block_threads_for(s.dim, cfg->method, records_dense(cfg->method, cfg->out_type));
     const long long traj_per_block = split_fn ? (long long)(block / 32) * kBuiltins[sys_id]->split_traj_per_warp : block;
     const long long blocks_all = (n + traj_per_block - 1) / traj_per_block;
@@ -483,8 +487,8 @@ static int launch_device(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg
         (ka.out.com_break == nullptr || ((uintptr_t)ka.out.com_coef & 15u) == 0)) {
         /* the split kernels stage recorded results per trajectory slot (whole rows of the result arrays:
          * 16-byte aligned whenever the arrays are) */
-        split_fn = kBuiltins[sys_id]->dop853_split_kernels[1][cfg->out_type];
-        dyn_smem = (size_t)(block / 32) * kBuiltins[sys_id]->split_traj_per_warp * kBuiltins[sys_id]->split_slot_bytes;
+        split_fn = split->fn[1][cfg->out_type];
+        dyn_smem = (size_t)(block / 32) * kBuiltins[sys_id]->split_traj_per_warp * split->slot_bytes;
     }
     CUDA_TRY(cudaMemsetAsync(ka.queue, 0, sizeof(unsigned long long), stream));
     if (stream == c->stream) CUDA_TRY(cudaEventRecord(c->ev0, stream));
@@ -492,7 +496,7 @@ static int launch_device(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg
         const void* fn = split_fn ? split_fn : kBuiltins[sys_id]->kernels[stage ? 1 : 0][cfg->method][cfg->out_type];
         if (ka.chunk_shift > 0) { /* host pipeline: the instantiation with its device side (never staged: see integrate_range) */
             if (stage || dyn_smem != 0) return fail(ODE_B200_ERR_INVALID_ARGUMENT, "internal: pipelined launch of a staged kernel");
-            fn = split_fn ? kBuiltins[sys_id]->dop853_split_pipe_kernels[cfg->out_type]
+            fn = split_fn ? split->pipe_fn[cfg->out_type]
                           : kBuiltins[sys_id]->pipe_kernels[cfg->method][cfg->out_type];
         }
         if (dyn_smem > 32 * 1024) /* static tables + dynamic rings may exceed the 48 KB default together */

@@ -17,13 +17,15 @@ struct SystemEntry {
     const void* pipe_kernels[3][4];
     /* the steppers with T = f32 by method (nullptr when the system's RHS is f64-only) */
     const void* f32_kernels[3];
-    /* Dop853 with one trajectory per group of three lanes (ode_split.cuh), by out_type; nullptr: the
-     * system has no split form and runs one trajectory per thread */
-    const void* dop853_split_kernels[2][4]; /* [results staged through shared memory: no, yes][out_type] */
-    int split_threads[4];         /* CTA size of each of them */
-    int split_traj_per_warp;      /* 10: lanes 30 and 31 stay idle */
-    int split_slot_bytes;         /* shared memory per trajectory slot of a staged launch */
-    const void* dop853_split_pipe_kernels[4]; /* unstaged, with the host pipeline's device side */
+    /* Dopri5 ([0]) and Dop853 ([1]) with one trajectory per group of three lanes (ode_split.cuh), by out_type;
+     * nullptr: the system has no split form and runs one trajectory per thread */
+    struct SplitKernels {
+        const void* fn[2][4];   /* [results staged through shared memory: no, yes][out_type] */
+        int threads[4];         /* CTA size of each of them */
+        int slot_bytes;         /* shared memory per trajectory slot of a staged launch */
+        const void* pipe_fn[4]; /* unstaged, with the host pipeline's device side */
+    } split[2];
+    int split_traj_per_warp; /* 10: lanes 30 and 31 stay idle */
 };
 
 }  // namespace ode_b200

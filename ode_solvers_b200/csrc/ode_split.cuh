@@ -167,31 +167,21 @@ ODE_DEV void gather_full_(const Lane3& L, const double (&loc)[SS::NS], double (&
     });
 }
 
-/* ============================================================================ Dop853, three lanes per trajectory */
-template <class SS, int OUT, bool STAGE = false>
-struct Dop853SplitStepper {
+/* ============================================================================ shared by the split steppers */
+/* State, result stores (direct or through the trajectory's shared-memory slot and the TMA engine), the checked
+ * right-hand side and hinit; M = coefficient rows per ContinuousOutputModel interval (Dopri5: 5, Dop853: 8) */
+template <class SS, bool STAGE, int M>
+struct SplitCommon {
     static constexpr int N = SS::NS, NF = SS::FULL;
     static constexpr bool kStage = STAGE;
     /* STAGE: recorded results leave through shared memory and the TMA engine. Every trajectory slot of
-     * the CTA owns 9 rows of NF doubles (8 coefficient rows of an interval + 1 sample row): the three lanes
+     * the CTA owns M + 1 rows of NF doubles (the coefficient rows of an interval + 1 sample row): the three lanes
      * write their components into the rows (the layout of the result arrays), and the group's first lane
-     * hands each block to the TMA engine as ONE bulk copy (1152 B of coefficients, 144 B of state) instead
+     * hands each block to the TMA engine as ONE bulk copy (Dop853: 1152 B of coefficients, 144 B of state) instead
      * of 54 scattered 8-byte stores per lane (ncu, direct stores: 16.3 GB written at 750 GB/s with
      * long-scoreboard and LSU-queue stalls on top). */
-    static constexpr int kSlotDoubles = 9 * NF;
-    static constexpr bool DENSE = OUT == ODE_B200_OUT_DENSE;
-    static constexpr bool CONT8 = OUT == ODE_B200_OUT_CONTINUOUS8;
-    /* one lockstep CTA per SM like the n = 6 kernels: 12 warps at 168 registers, 8 warps with all 255 when the
-     * dense-output coefficients are live as well (-D overrides for measurements) */
-#ifndef ODE_B200_SPLIT_THREADS_SPARSE
-#define ODE_B200_SPLIT_THREADS_SPARSE ODE_B200_LOCK_THREADS
-#endif
-#ifndef ODE_B200_SPLIT_THREADS_DENSE
-#define ODE_B200_SPLIT_THREADS_DENSE 256
-#endif
-    static constexpr int kThreads = (DENSE || CONT8) ? ODE_B200_SPLIT_THREADS_DENSE : ODE_B200_SPLIT_THREADS_SPARSE;
+    static constexpr int kSlotDoubles = (M + 1) * NF;
     static constexpr int kSlotsPerWarp = 10;
-    static constexpr int kRefillIdle = ODE_B200_REFILL_IDLE;
     static_assert(!SS::HAS_SOLOUT, "solout of a split system is not implemented");
 
     struct State {
@@ -230,7 +220,7 @@ struct Dop853SplitStepper {
             const size_t q = (size_t)s.traj * (size_t)a.out_pitch + s.c.out_count;
             if (L.role == 0u) a.out.out_x[q] = x;
             if constexpr (STAGE) {
-                double* b = slot_(L) + 8 * NF;
+                double* b = slot_(L) + M * NF;
                 slot_acquire_(L);
 #pragma unroll
                 for (int c = 0; c < N; ++c) b[SS::gcomp(L.role, c)] = y[c];
@@ -250,7 +240,7 @@ struct Dop853SplitStepper {
     }
     /* Continuous8: the sample (x, y) and the interval (|x|, rcont[0..7], h_old) of one accepted step */
     ODE_DEV static void push_step(const KernelArgs& a, State& s, const Lane3& L, double x, const double (&y)[N],
-                                  double brk, double step, const double (&rc)[8][N]) {
+                                  double brk, double step, const double (&rc)[M][N]) {
         const ode_b200_outputs& o = a.out;
         const bool rec_y = o.out_x != nullptr && (long long)s.c.out_count < o.out_cap;
         const bool rec_c = o.com_break != nullptr && (long long)s.c.com_count < o.com_cap;
@@ -268,17 +258,17 @@ struct Dop853SplitStepper {
                 double* b = slot_(L);
                 slot_acquire_(L);
 #pragma unroll
-                for (int c = 0; c < N; ++c) b[8 * NF + SS::gcomp(L.role, c)] = y[c];
+                for (int c = 0; c < N; ++c) b[M * NF + SS::gcomp(L.role, c)] = y[c];
                 if (rec_c) {
 #pragma unroll
-                    for (int r = 0; r < 8; ++r)
+                    for (int r = 0; r < M; ++r)
 #pragma unroll
                         for (int c = 0; c < N; ++c) b[r * NF + SS::gcomp(L.role, c)] = rc[r][c];
                 }
                 slot_release_(L);
                 if (L.role == 0u) {
-                    if (rec_c) bulk_(o.com_coef + qc * (8 * NF), b, 8 * NF * 8);
-                    if (rec_y) bulk_(o.out_y + qy * NF, b + 8 * NF, NF * 8);
+                    if (rec_c) bulk_(o.com_coef + qc * (M * NF), b, M * NF * 8);
+                    if (rec_y) bulk_(o.out_y + qy * NF, b + M * NF, NF * 8);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
@@ -289,15 +279,15 @@ struct Dop853SplitStepper {
             }
             if (rec_c) {
 #pragma unroll
-                for (int r = 0; r < 8; ++r)
+                for (int r = 0; r < M; ++r)
 #pragma unroll
-                    for (int c = 0; c < N; ++c) o.com_coef[(qc * 8 + r) * NF + SS::gcomp(L.role, c)] = rc[r][c];
+                    for (int c = 0; c < N; ++c) o.com_coef[(qc * M + r) * NF + SS::gcomp(L.role, c)] = rc[r][c];
             }
         }
         s.c.out_count += 1;
         s.c.com_count += 1;
     }
-    ODE_DEV static void finish(State& s, const KernelArgs& a, const Lane3& L, int status) {
+    ODE_DEV static void finish_(State& s, const KernelArgs& a, const Lane3& L, int status, double com_lower) {
         const ode_b200_outputs& o = a.out;
         const long long t = s.traj;
         if (status == ODE_B200_OK && ((o.out_cap > 0 && (long long)s.c.out_count > o.out_cap) ||
@@ -316,22 +306,10 @@ struct Dop853SplitStepper {
             if (o.status) o.status[t] = status;
             if (o.out_count) o.out_count[t] = s.c.out_count;
             if (o.com_count) o.com_count[t] = s.c.com_count;
-            if (o.com_lower) o.com_lower[t] = CONT8 ? a.cfg.x0 : 0.0;
+            if (o.com_lower) o.com_lower[t] = com_lower;
             /* the slot goes to the next trajectory only after the TMA engine has read it */
             if constexpr (STAGE) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
-    }
-
-    /* compute_y_out, dop853.rs:546-559 */
-    ODE_DEV static void y_out(const double (&rc)[8][N], double th, double th1, double (&o)[N]) {
-#pragma unroll
-        for (int i = 0; i < N; ++i)
-            o[i] = rc[0][i] +
-                   (rc[1][i] +
-                    (rc[2][i] +
-                     (rc[3][i] + (rc[4][i] + (rc[5][i] + (rc[6][i] + rc[7][i] * th) * th1) * th) * th1) * th) *
-                        th1) *
-                       th;
     }
 
     /* ---- right-hand side with its own check, executed by the whole warp: `use` marks the lanes whose
@@ -364,8 +342,9 @@ struct Dop853SplitStepper {
         }
     }
 
-    /* ---- hinit (dop853.rs:195-251), norms in index order over the full state; whole warp */
-    ODE_DEV static double hinit(const KernelArgs& a, const Lane3& L, double x, const double (&y)[N], const double (&pl)[2]) {
+    /* ---- hinit (dopri5.rs:187-243, dop853.rs:195-251), norms in index order over the full state; whole warp */
+    ODE_DEV static double hinit(const KernelArgs& a, const Lane3& L, double x, const double (&y)[N], const double (&pl)[2],
+                                double expo) {
         double f0[N], f1[N], y1[N], t0[N], t1[N];
         MathExact mx;
         SS::rhs(L, x, y, f0, pl, mx);
@@ -398,12 +377,13 @@ struct Dop853SplitStepper {
         if (fmax(sqrt(d1), fabs(d2)) <= 1.0E-15)
             h1 = fmax(1.0E-6, fabs(h0) * 1.0E-3);
         else
-            h1 = pow_d(0.01 / fmax(sqrt(d1), d2), 0.125); /* second d2 without abs, as in the source */
+            h1 = pow_d(0.01 / fmax(sqrt(d1), d2), expo); /* second d2 without abs, as in the source */
         return sign_(fmin(100.0 * fabs(h0), fmin(h1, a.h_max_abs)), posneg);
     }
 
-    /* ---- prologue of the trajectories the lanes with `ok` have just claimed (dop853.rs:255-278); whole warp */
-    ODE_DEV static void init_all(State& s, const KernelArgs& a, long long t, bool ok, const Lane3& L) {
+    /* ---- what both prologues share (dopri5.rs:268-296, dop853.rs:255-278): the claimed trajectory's inputs,
+     * hinit when h0 == 0, k0 = f(x0, y0); whole warp, only lanes with `ok` commit */
+    ODE_DEV static void prologue_(State& s, const KernelArgs& a, long long t, bool ok, const Lane3& L, double expo) {
         const long long tt = ok ? t : 0; /* lanes that commit nothing still load from a valid row */
         double y[N], pl[2], k0[N];
 #pragma unroll
@@ -415,7 +395,7 @@ struct Dop853SplitStepper {
         double h = a.cfg.h0;
         unsigned num_eval = 0;
         if (h == 0.0) { /* batch-uniform */
-            h = hinit(a, L, x, y, pl);
+            h = hinit(a, L, x, y, pl, expo);
             num_eval += 2;
         }
         rhs_checked(L, ok, x, y, k0, pl);
@@ -436,8 +416,62 @@ struct Dop853SplitStepper {
             s.iasti = s.non_stiff = s.stiff_ctr = 0;
             s.h = h;
             s.h_old = h;
+        }
+    }
+};
+
+/* ============================================================================ Dop853, three lanes per trajectory */
+template <class SS, int OUT, bool STAGE = false>
+struct Dop853SplitStepper : SplitCommon<SS, STAGE, 8> {
+    using C = SplitCommon<SS, STAGE, 8>;
+    using typename C::State;
+    using C::N;
+    using C::NF;
+    using C::kStage;
+    using C::kSlotDoubles;
+    using C::kSlotsPerWarp;
+    using C::slot_;
+    using C::slot_acquire_;
+    using C::slot_release_;
+    using C::bulk_;
+    using C::push;
+    using C::push_step;
+    using C::rhs_checked;
+    static constexpr bool DENSE = OUT == ODE_B200_OUT_DENSE;
+    static constexpr bool CONT8 = OUT == ODE_B200_OUT_CONTINUOUS8;
+    /* one lockstep CTA per SM like the n = 6 kernels: 12 warps at 168 registers, 8 warps with all 255 when the
+     * dense-output coefficients are live as well (-D overrides for measurements) */
+#ifndef ODE_B200_SPLIT_THREADS_SPARSE
+#define ODE_B200_SPLIT_THREADS_SPARSE ODE_B200_LOCK_THREADS
+#endif
+#ifndef ODE_B200_SPLIT_THREADS_DENSE
+#define ODE_B200_SPLIT_THREADS_DENSE 256
+#endif
+    static constexpr int kThreads = (DENSE || CONT8) ? ODE_B200_SPLIT_THREADS_DENSE : ODE_B200_SPLIT_THREADS_SPARSE;
+    static constexpr int kRefillIdle = ODE_B200_REFILL_IDLE;
+
+    ODE_DEV static void finish(State& s, const KernelArgs& a, const Lane3& L, int status) {
+        C::finish_(s, a, L, status, CONT8 ? a.cfg.x0 : 0.0);
+    }
+
+    /* compute_y_out, dop853.rs:546-559 */
+    ODE_DEV static void y_out(const double (&rc)[8][N], double th, double th1, double (&o)[N]) {
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            o[i] = rc[0][i] +
+                   (rc[1][i] +
+                    (rc[2][i] +
+                     (rc[3][i] + (rc[4][i] + (rc[5][i] + (rc[6][i] + rc[7][i] * th) * th1) * th) * th1) * th) *
+                        th1) *
+                       th;
+    }
+
+    /* ---- prologue of the trajectories the lanes with `ok` have just claimed (dop853.rs:255-278); whole warp */
+    ODE_DEV static void init_all(State& s, const KernelArgs& a, long long t, bool ok, const Lane3& L) {
+        C::prologue_(s, a, t, ok, L, 0.125);
+        if (ok) {
             /* solution_output(y0), dop853.rs:273-274 -> :515-519 / :541 */
-            push(a, s, L, x, y);
+            push(a, s, L, s.x, s.y);
             if constexpr (DENSE) s.xd += a.cfg.dx; /* first call: |xd - x0| = 0 < EPSILON always */
         }
     }
@@ -850,6 +884,291 @@ struct Dop853SplitStepper {
                 push(a, s, L, cfg.x0, s.y); /* pushes x0, not x (Q6) */
             }
             if (last) { /* dop853.rs:499-502 */
+                s.h_old = a.posneg * h_new;
+                finish(s, a, L, ODE_B200_OK);
+                active = false;
+                return;
+            }
+            s.h = h_new;
+        }
+    }
+};
+
+/* ============================================================================ Dopri5, three lanes per trajectory */
+/* Per component the statements of Dopri5Stepper (ode_kernels.cuh); only the error norm and the stiffness quotient
+ * cross the lanes. Dopri5 has no extra dense-output stages, so everything after the attempt's straight-line block
+ * except the (rare) stiffness test runs per lane. */
+template <class SS, int OUT, bool STAGE = false>
+struct Dopri5SplitStepper : SplitCommon<SS, STAGE, 5> {
+    using C = SplitCommon<SS, STAGE, 5>;
+    using typename C::State;
+    using C::N;
+    using C::NF;
+    using C::kStage;
+    using C::kSlotDoubles;
+    using C::kSlotsPerWarp;
+    using C::push;
+    using C::push_step;
+    static constexpr bool DENSE = OUT == ODE_B200_OUT_DENSE;
+    static constexpr bool CONT = OUT == ODE_B200_OUT_CONTINUOUS;
+#ifndef ODE_B200_SPLIT5_THREADS_SPARSE
+#define ODE_B200_SPLIT5_THREADS_SPARSE ODE_B200_LOCK_THREADS
+#endif
+#ifndef ODE_B200_SPLIT5_THREADS_DENSE
+#define ODE_B200_SPLIT5_THREADS_DENSE ODE_B200_LOCK_THREADS
+#endif
+    static constexpr int kThreads = (DENSE || CONT) ? ODE_B200_SPLIT5_THREADS_DENSE : ODE_B200_SPLIT5_THREADS_SPARSE;
+    static constexpr int kRefillIdle = ODE_B200_REFILL_IDLE;
+
+    ODE_DEV static void finish(State& s, const KernelArgs& a, const Lane3& L, int status) {
+        C::finish_(s, a, L, status, a.cfg.x0);
+    }
+
+    /* compute_y_out, dopri5.rs:490-495 */
+    ODE_DEV static void y_out(const double (&rc)[5][N], double th, double th1, double (&o)[N]) {
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            o[i] = rc[0][i] + (rc[1][i] + (rc[2][i] + (rc[3][i] + rc[4][i] * th1) * th) * th1) * th;
+    }
+
+    /* ---- prologue (dopri5.rs:268-296): only Sparse records y0 here; whole warp */
+    ODE_DEV static void init_all(State& s, const KernelArgs& a, long long t, bool ok, const Lane3& L) {
+        C::prologue_(s, a, t, ok, L, 1.0 / 5.0);
+        if constexpr (OUT == ODE_B200_OUT_SPARSE) {
+            if (ok) push(a, s, L, s.x, s.y);
+        }
+    }
+
+    struct Work {
+        double k[7][N]; /* k[0] = f(x, y); k[s] for s = 1..6, k[6] is the reference's new k[1] */
+        double ynext[N];
+        double err;
+        CtrlEval ce;
+    };
+    struct ColdIn {
+        double y[N], k0[N], pl[2], x, h, pw_old;
+    };
+
+    /* the straight-line block of one attempt; whole warp. Same statements per component as Dopri5Stepper::core */
+    template <class M>
+    ODE_DEV static void core(const Lane3& L, const double (&y)[N], const double (&k0)[N], const double (&pl)[2],
+                             double pw_old, const KernelArgs& a, double x, double h, Work& w, M& m) {
+        const ode_b200_config& cfg = a.cfg;
+        double(&k)[7][N] = w.k;
+        double(&ynext)[N] = w.ynext;
+        bool bad = false;
+#pragma unroll
+        for (int i = 0; i < N; ++i) k[0][i] = k0[i];
+        static_for<1, 7>([&](auto S) { /* 6 stages, dopri5.rs:326-340 */
+            constexpr int sg = decltype(S)::value;
+#pragma unroll
+            for (int i = 0; i < N; ++i) ynext[i] = y[i];
+            static_for<0, sg>([&](auto J) {
+                constexpr int j = decltype(J)::value;
+                constexpr double aij = TabDp5::a(sg, j);
+                if constexpr (aij != 0.0) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) ynext[i] = ynext[i] + (k[j][i] * h) * c_dp5_a[sg][j];
+                }
+            });
+            SS::rhs(L, x + h * c_dp5_c[sg], ynext, k[sg], pl, m);
+            if constexpr (sg == 1) { /* only k2 meets structural zeros (see the header note of ode_kernels.cuh) */
+#pragma unroll
+                for (int i = 0; i < N; ++i) bad |= nonfinite_(k[sg][i]);
+            }
+        });
+        /* error estimate and norm, dopri5.rs:354-371: err += (e_i / sc_i)^2 over i = 0..n-1 in index order */
+        double t[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double ee = (((((k[0][i] * c_dp5_e[0] + k[2][i] * c_dp5_e[2]) + k[3][i] * c_dp5_e[3]) +
+                                 k[4][i] * c_dp5_e[4]) +
+                                k[5][i] * c_dp5_e[5]) +
+                               k[6][i] * c_dp5_e[6]) *
+                              h;
+            const double sc = cfg.atol + fmax(fabs(y[i]), fabs(ynext[i])) * cfg.rtol;
+            const double q = m.div(ee, sc);
+            t[i] = q * q;
+        }
+        double err = ordered_sum_<SS>(L, t);
+        err = m.sqrt(m.div(err, (double)NF));
+        if (group_any_(L, bad)) err = qnan_();
+        w.err = err;
+        ctrl_eval_(pw_old, a, err, h, m, w.ce);
+    }
+
+    static __device__ __noinline__ void core_exact(const Lane3* L, const ColdIn* in, const KernelArgs* a, Work* w) {
+        MathExact m;
+        core<MathExact>(*L, in->y, in->k0, in->pl, in->pw_old, *a, in->x, in->h, *w, m);
+    }
+
+    /* one pass of `while !last` (dopri5.rs:299-443) for every lane of the warp; `active` lanes hold a trajectory */
+    ODE_DEV static void attempt_all(State& s, const KernelArgs& a, bool& active, const Lane3& L) {
+        const ode_b200_config& cfg = a.cfg;
+        /* ---- per lane: the two abort tests and the clamp of the last step */
+        bool go = active, last = false;
+        if (active) {
+            int fin = -1;
+            if (s.c.n_step > cfg.n_max) /* '>' here, '>=' in dop853 (Q2) */
+                fin = ODE_B200_MAX_NUM_STEP_REACHED;
+            else if (0.1 * fabs(s.h) <= cfg.uround * fabs(s.x))
+                fin = ODE_B200_STEP_SIZE_UNDERFLOW;
+            if (fin >= 0) {
+                s.h_old = s.h;
+                finish(s, a, L, fin);
+                active = go = false;
+            } else {
+                if ((s.x + 1.01 * s.h - cfg.x_end) * a.posneg > 0.0) {
+                    s.h = cfg.x_end - s.x;
+                    last = true;
+                }
+                s.c.n_step += 1;
+            }
+        }
+        if (!__any_sync(kFullMask, go)) return;
+        const double h = s.h, x = s.x;
+
+        /* ---- whole warp: the attempt */
+        Work w;
+        MathFast m;
+        core<MathFast>(L, s.y, s.k0, s.pl, s.ctrl.pw_old, a, x, h, w, m);
+        if (__builtin_expect(__any_sync(kFullMask, go && m.bad()), 0)) {
+            ColdIn in;
+            Work w2;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                in.y[i] = s.y[i];
+                in.k0[i] = s.k0[i];
+            }
+            in.pl[0] = s.pl[0];
+            in.pl[1] = s.pl[1];
+            in.x = x;
+            in.h = h;
+            in.pw_old = s.ctrl.pw_old;
+            core_exact(&L, &in, &a, &w2);
+            w = w2;
+        }
+        double(&k)[7][N] = w.k;
+        double(&ynext)[N] = w.ynext;
+
+        /* ---- per lane: controller */
+        double h_new = 0.0;
+        bool acc = false;
+        if (go) {
+            s.c.num_eval += 6;
+            acc = ctrl_commit_(s.ctrl, a, w.ce, w.err, h, h_new);
+            if (acc) {
+                s.c.accepted += 1;
+            } else {
+                if (s.c.accepted >= 1) s.c.rejected += 1; /* Q5 */
+                s.h = h_new;
+            }
+        }
+        /* ---- stiffness detection (dopri5.rs:378-402): rare, whole warp when any lane is due */
+        bool due = false;
+        if (acc) {
+            if (++s.stiff_ctr == cfg.n_stiff) s.stiff_ctr = 0;
+            due = s.stiff_ctr == 0 || s.iasti > 0;
+        }
+        if (__builtin_expect(__any_sync(kFullMask, due), 0)) {
+            /* y_stiff = the argument of stage 6, rebuilt from the still-live k1..k5 (see Dopri5Stepper::attempt) */
+            double ystiff[N], d1[N], d2[N], f1[NF], f2[NF];
+#pragma unroll
+            for (int i = 0; i < N; ++i) ystiff[i] = s.y[i];
+            static_for<0, 5>([&](auto J) {
+                constexpr int j = decltype(J)::value;
+                if constexpr (TabDp5::a(5, j) != 0.0) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) ystiff[i] = ystiff[i] + (k[j][i] * h) * c_dp5_a[5][j];
+                }
+            });
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                d1[i] = k[6][i] - k[5][i];
+                d2[i] = ynext[i] - ystiff[i];
+            }
+            gather_full_<SS>(L, d1, f1);
+            gather_full_<SS>(L, d2, f2);
+            if (due) {
+                const double num = sq_dot_<NF>(f1), den = sq_dot_<NF>(f2);
+                const double h_lamb = den > 0.0 ? h * sqrt(num / den) : 0.0;
+                if (h_lamb > 3.25) {
+                    s.iasti += 1;
+                    s.non_stiff = 0;
+                    if (s.iasti == 15) {
+                        s.h_old = h;
+                        finish(s, a, L, ODE_B200_STIFFNESS_DETECTED);
+                        active = acc = false;
+                    }
+                } else {
+                    s.non_stiff += 1;
+                    if (s.non_stiff == 6) s.iasti = 0;
+                }
+            }
+        }
+
+        /* ---- per lane: dense coefficients, commit of the accepted step, outputs, exit */
+        if (acc) {
+            double rc[5][N];
+            if constexpr (DENSE || CONT) { /* dopri5.rs:343-351 and :405-414 */
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    rc[4][i] = (((((k[0][i] * c_dp5_d[0] + k[2][i] * c_dp5_d[2]) + k[3][i] * c_dp5_d[3]) +
+                                  k[4][i] * c_dp5_d[4]) +
+                                 k[5][i] * c_dp5_d[5]) +
+                                k[6][i] * c_dp5_d[6]) *
+                               h;
+                    const double ydiff = ynext[i] - s.y[i];
+                    const double bspl = k[0][i] * h - ydiff;
+                    rc[0][i] = s.y[i];
+                    rc[1][i] = ydiff;
+                    rc[2][i] = bspl;
+                    rc[3][i] = ((-k[6][i]) * h + ydiff) - bspl;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                s.k0[i] = k[6][i];
+                s.y[i] = ynext[i];
+            }
+            s.x_old = x;
+            s.x = x + h;
+            s.h_old = h;
+            if constexpr (DENSE) { /* solution_output, dopri5.rs:447-487 */
+                bool unsupported = false;
+                double yo[N];
+                const double rh = div_rcp_(s.h_old);
+                const bool h_ok = div_in_range_(s.h_old);
+                while (fabs(s.xd) <= fabs(s.x)) {
+                    bool pushed = false;
+                    if (fabs(s.x_old) <= fabs(s.xd) && fabs(s.x) >= fabs(s.xd)) {
+                        const double th = div_with_rcp_(s.xd - s.x_old, s.h_old, rh, h_ok), th1 = 1.0 - th;
+                        y_out(rc, th, th1, yo);
+                        push(a, s, L, s.xd, yo);
+                        s.xd += cfg.dx;
+                        pushed = true;
+                    }
+                    if (s.c.out_count == 0) { unsupported = true; break; } /* reference: unwrap() on empty */
+                    /* the reference never returns (see Dopri5Stepper::attempt) */
+                    if (!pushed || cfg.dx == 0.0 || s.c.out_count > (1u << 26)) { unsupported = true; break; }
+                }
+                if (!unsupported && fabs(s.xd - cfg.x_end) < 1.0e-9) { /* endpoint rule, dopri5.rs:472-478 (Q9) */
+                    const double th = div_with_rcp_(cfg.x_end - s.x_old, s.h_old, rh, h_ok), th1 = 1.0 - th;
+                    y_out(rc, th, th1, yo);
+                    push(a, s, L, cfg.x_end, yo);
+                    s.xd += cfg.dx;
+                }
+                if (unsupported || s.c.out_count == 0) {
+                    finish(s, a, L, ODE_B200_UNSUPPORTED_DOMAIN);
+                    active = false;
+                    return;
+                }
+            } else if constexpr (CONT) { /* the sample, then add_interval(|x|, rcont, h_old), dopri5.rs:484-486 */
+                push_step(a, s, L, s.x, s.y, fabs(s.x), s.h_old, rc);
+            } else {
+                push(a, s, L, s.x, s.y);
+            }
+            if (last) { /* normal exit, dopri5.rs:432-435 */
                 s.h_old = a.posneg * h_new;
                 finish(s, a, L, ODE_B200_OK);
                 active = false;

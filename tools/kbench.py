@@ -63,6 +63,14 @@ def build(name, n):
         y0, p = W.threebody18_ensemble(n)
         return ("threebody18", ob.config_new(ob.DOP853, 0.0, 5.0, 0.1, 1e-9, 1e-9, out_type=ob.OUT_CONTINUOUS8), y0, p,
                 -120, 3708 + 153 * 18 + 3 * 90)
+    if name == "threebody18_dp5":       # 6 RHS of ~90 flops + 20 stage terms x 3 x 18 + error norm ~18 x 18
+        y0, p = W.threebody18_ensemble(n)
+        return ("threebody18", ob.config_new(ob.DOPRI5, 0.0, 5.0, 0.1, 1e-9, 1e-9, out_type=ob.OUT_SPARSE), y0, p, 0,
+                1944)
+    if name == "threebody18_dp5_com":   # every accepted step + its ContinuousOutputModel interval (5 x 18 + 2 doubles)
+        y0, p = W.threebody18_ensemble(n)
+        return ("threebody18", ob.config_new(ob.DOPRI5, 0.0, 5.0, 0.1, 1e-9, 1e-9, out_type=ob.OUT_CONTINUOUS), y0, p,
+                -300, 1944 + 14 * 18)
     if name == "robertson_dp8":
         y0, p = W.robertson_sweep(n)
         return ("robertson", ob.config_new(ob.DOP853, 0.0, 0.3, 0.3, 1e-2, 1e-6, out_type=ob.OUT_SPARSE), y0, p, 0,
