@@ -125,7 +125,7 @@ class Context:
         _check(self._lib.ode_b200_set_pipeline(self.handle, int(chunk_log2)), "set_pipeline")
 
     def set_lane_split(self, enabled):
-        """large states (threebody18 / Dop853): one trajectory per group of three lanes (default) or per thread"""
+        """large states (threebody18, Dopri5 / Dop853): one trajectory per group of three lanes (default) or per thread"""
         _check(self._lib.ode_b200_set_lane_split(self.handle, int(bool(enabled))), "set_lane_split")
 
     @property

@@ -1,5 +1,5 @@
 /*
- * ode_split.cuh -- Dop853 for LARGE states (n = 18): one trajectory per GROUP OF THREE LANES.
+ * ode_split.cuh -- Dopri5 and Dop853 for LARGE states (n = 18): one trajectory per GROUP OF THREE LANES.
  *
  * One trajectory per thread keeps k[12][n] in registers; for n = 18 that is 432 registers of stage
  * values alone, and the round-1 kernel streamed them through local memory (ncu: 20 GB of DRAM writes
@@ -23,7 +23,7 @@
  * itself, the prologue of newly claimed trajectories, the three extra dense stages) in which lanes
  * without work compute on stale values and commit nothing.
  *
- * Bit parity: per component the operations and their order are those of Dop853Stepper
+ * Bit parity: per component the operations and their order are those of Dopri5Stepper / Dop853Stepper
  * (ode_kernels.cuh), which the parity tests hold bit for bit against the oracle; the only new
  * arithmetic is the order of the cross-component sums, reproduced exactly as described above.
  */
