@@ -19,6 +19,11 @@
  * separate * and + is a separate vmulsd/vaddsd. nvcc is run with -fmad=false so nothing
  * else fuses on the device; gcc hosts must use -ffp-contract=off.
  *
+ * Upstream and licence: the algorithm is that of ARM Optimized Routines (math/pow.c, math/exp.c, math/powf.c;
+ * MIT OR Apache-2.0 WITH LLVM-exception), which glibc ships under the LGPL-2.1-or-later in sysdeps/ieee754.
+ * This file is a restatement written from the published algorithm and the observed machine code, not a copy of
+ * either source; the numeric tables are data read at build time from the libm installed on the build host.
+ *
  * tests/test_pow_clone.py (CPU) and tests/test_gpu_pow.py (device) check bit equality with
  * libm over the controller's domain, the full double range and all special cases.
  */

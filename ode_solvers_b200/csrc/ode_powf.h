@@ -12,6 +12,11 @@
  * the machine code of glibc's FMA build (__powf_fma): every a*b+c of log2_inline and exp2_inline is one
  * vfmadd; r = xd - kd and the final y * s are a separate vsubsd / vmulsd.
  *
+ * Upstream and licence: the algorithm is that of ARM Optimized Routines (math/pow.c, math/exp.c, math/powf.c;
+ * MIT OR Apache-2.0 WITH LLVM-exception), which glibc ships under the LGPL-2.1-or-later in sysdeps/ieee754.
+ * This file is a restatement written from the published algorithm and the observed machine code, not a copy of
+ * either source; the numeric tables are data read at build time from the libm installed on the build host.
+ *
  * tests/test_pow_clone.py checks bit equality with libm's powf on the host; the device build is the
  * same source compiled with -fmad=false (explicit fma() only).
  */
