@@ -1161,7 +1161,14 @@ extern "C" int ode_b200_measure_fp64_peak(int device, double* inst_per_s, double
  * Bit parity: theta = (x - lower) / step, then r = c[m-1]; r = c[q] + r * (q even ? theta : 1 - theta), as the source.
  */
 constexpr int kComWarps = 8;     /* warps (= models) per CTA */
-constexpr int kComCoarse = 192;  /* entries of a model's coarse breakpoint index in shared memory */
+#ifndef ODE_B200_COM_COARSE
+#define ODE_B200_COM_COARSE 192
+#endif
+#ifndef ODE_B200_COM_BLOCKS
+#define ODE_B200_COM_BLOCKS 6
+#endif
+constexpr int kComCoarse = ODE_B200_COM_COARSE; /* entries of a model's coarse breakpoint index in shared memory */
+constexpr int kComBlocks = ODE_B200_COM_BLOCKS; /* CTAs per SM */
 
 /* first index in [lo, hi) whose breakpoint is >= x (hi if none): the match of the reference's binary_search_by
  * (breakpoints are strictly increasing), or its insertion point */
@@ -1178,7 +1185,7 @@ __device__ __forceinline__ unsigned com_lower_bound_(unsigned lo, unsigned hi, d
 }
 
 template <int M, int D>
-__global__ void __launch_bounds__(kComWarps * 32, 6) com_evaluate_kernel(long long n, int dim_rt, int m_rt, long long cap,
+__global__ void __launch_bounds__(kComWarps * 32, kComBlocks) com_evaluate_kernel(long long n, int dim_rt, int m_rt, long long cap,
                                                                          const double* __restrict__ lower,
                                                                          const double* __restrict__ brk,
                                                                          const double* __restrict__ stp,
@@ -1206,43 +1213,45 @@ __global__ void __launch_bounds__(kComWarps * 32, 6) com_evaluate_kernel(long lo
         const double lb0 = lower[t];
         for (long long q0 = 0; q0 < nq; q0 += 32) {
             const long long qi = q0 + lane;
-            if (qi >= nq) continue;
-            const double x = xq[qi];
-            unsigned char ok = 0;
-            const long long qo = perm ? (long long)perm[qi] : qi; /* host entry: xq sorted, results back in the caller's order */
-            double* yo = y + ((size_t)t * nq + qo) * dim;
-            if (!(x < lb0) && m > 0 && x == x) { /* x < lower_bound -> None; NaN: partial_cmp().unwrap() panics */
+            const bool have = qi < nq;
+            const double x = have ? xq[qi] : 0.0;
+            const long long qo = have ? (perm ? (long long)perm[qi] : qi) : 0; /* host entry: xq sorted, results in the caller's order */
+            unsigned lo = cnt;
+            if (have && !(x < lb0) && m > 0 && x == x) { /* x < lower_bound -> None; NaN: partial_cmp().unwrap() panics */
                 /* block j holds breakpoints [j s, min((j + 1) s, cnt)); its last one is s_idx[j]: the first block whose
                  * last breakpoint is >= x contains the answer */
                 const unsigned j = com_lower_bound_(0u, nc, x, [&](unsigned k) { return s_idx[w][k]; });
-                unsigned lo = cnt;
                 if (j < nc) lo = com_lower_bound_(j * s, min((j + 1u) * s, cnt) - 1u, x, [&](unsigned k) { return __ldg(bp + k); });
-                if (lo < cnt) {
-                    const double lb = lo == 0 ? lb0 : __ldg(bp + lo - 1);
-                    const double theta = (x - lb) / __ldg(stp + (size_t)t * cap + lo), theta1 = 1.0 - theta;
-                    const double* c = coef + ((size_t)t * cap + lo) * m * dim;
-                    if constexpr (M > 0 && D > 0) {
-                        double r[D];
+            }
+            const bool hit = have && lo < cnt;
+            if (hit) {
+                double* yo = y + ((size_t)t * nq + qo) * dim;
+                const double lb = lo == 0 ? lb0 : __ldg(bp + lo - 1);
+                const double theta = (x - lb) / __ldg(stp + (size_t)t * cap + lo), theta1 = 1.0 - theta;
+                if constexpr (M > 0 && D > 0) {
+                    double r[D];
+                    auto horner = [&](const double* c) {
 #pragma unroll
                         for (int i = 0; i < D; ++i) r[i] = __ldg(c + (M - 1) * D + i);
 #pragma unroll
                         for (int k = M - 2; k >= 0; --k)
 #pragma unroll
                             for (int i = 0; i < D; ++i) r[i] = __ldg(c + k * D + i) + r[i] * ((k % 2 == 0) ? theta : theta1);
+                    };
+                    horner(coef + ((size_t)t * cap + lo) * (M * D));
 #pragma unroll
-                        for (int i = 0; i < D; ++i) yo[i] = r[i];
-                    } else {
-                        for (int i = 0; i < dim; ++i) {
-                            double r = __ldg(c + (size_t)(m - 1) * dim + i);
-                            for (int k = m - 2; k >= 0; --k)
-                                r = __ldg(c + (size_t)k * dim + i) + r * ((k % 2 == 0) ? theta : theta1);
-                            yo[i] = r;
-                        }
+                    for (int i = 0; i < D; ++i) yo[i] = r[i];
+                } else {
+                    const double* c = coef + ((size_t)t * cap + lo) * m * dim;
+                    for (int i = 0; i < dim; ++i) {
+                        double r = __ldg(c + (size_t)(m - 1) * dim + i);
+                        for (int k = m - 2; k >= 0; --k)
+                            r = __ldg(c + (size_t)k * dim + i) + r * ((k % 2 == 0) ? theta : theta1);
+                        yo[i] = r;
                     }
-                    ok = 1;
                 }
             }
-            found[(size_t)t * nq + qo] = ok;
+            if (have) found[(size_t)t * nq + qo] = hit ? 1 : 0;
         }
     }
 }
@@ -1270,7 +1279,7 @@ static int com_validate(ode_b200_ctx* c, int64_t n, int dim, int m, int64_t cap,
 static int com_launch(ode_b200_ctx* c, int64_t n, int dim, int m, int64_t cap, const double* lower, const double* brk,
                       const double* stp, const double* coef, const uint32_t* count, int64_t nq, const double* xq, double* y,
                       uint8_t* found, const unsigned* perm, cudaStream_t st) {
-    const long long blocks = std::min<long long>((n + kComWarps - 1) / kComWarps, (long long)c->num_sms * 6);
+    const long long blocks = std::min<long long>((n + kComWarps - 1) / kComWarps, (long long)c->num_sms * kComBlocks);
     com_kernel_for(m, dim)<<<(unsigned)blocks, kComWarps * 32, 0, st>>>(n, dim, m, cap, lower, brk, stp, coef, count, nq, xq, y,
                                                                       found, perm);
     c->launches++;
