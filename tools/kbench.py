@@ -81,6 +81,22 @@ def build(name, n):
     raise SystemExit("unknown workload " + name)
 
 
+def f32_rows(n, reps, ctx):
+    """the T = f32 steppers (csrc/ode_f32.cuh) on the Lorenz ensemble; tolerances f32 can reach"""
+    y0, p = W.lorenz_ensemble(n)
+    f = ob.System.builtin("lorenz")
+    for name, cfg in (("lorenz_dp5_f32", ob.config_new_f32(ob.DOPRI5, 0.0, 20.0, 0.1, 1e-4, 1e-4, out_type=ob.OUT_SPARSE)),
+                      ("lorenz_dp8_f32", ob.config_new_f32(ob.DOP853, 0.0, 20.0, 0.1, 1e-4, 1e-4, out_type=ob.OUT_SPARSE)),
+                      ("lorenz_rk4_f32", ob.config_rk4_f32(0.0, 2.0, 1e-3))):
+        best = 1e30
+        for _ in range(reps):
+            o = ob.integrate_batch_f32(f, cfg, y0.astype(np.float32), p.astype(np.float32), ctx=ctx)
+            best = min(best, o.kernel_ms)
+        acc = int(o.accepted.sum())
+        print("%-18s n=%d kernel %.3f ms  %.3e acc-steps/s  acc/att=%d/%d bad=%d" % (
+            name, n, best, acc / best * 1e3, acc, int(o.n_step.sum()), int((o.status != 0).sum())), flush=True)
+
+
 def main():
     names = sys.argv[1:] or ["lorenz_dp5", "lorenz_dp8", "kepler_dp8"]
     n = int(os.environ.get("KBENCH_N", 1 << 20))
@@ -92,6 +108,9 @@ def main():
     for q in (1, 0) if os.environ.get("KBENCH_STATIC") else (1,):
         ctx.set_work_queue(bool(q))
         for name in names:
+            if name == "f32":
+                f32_rows(n, reps, ctx)
+                continue
             nn = n if not any(k in name for k in ("threebody", "dense", "all_steps", "com")) else min(n, 1 << 18)
             sysname, cfg, y0, p, cap, flops = build(name, nn)
             f = ob.System.builtin(sysname)
