@@ -55,13 +55,22 @@ def test_cpp_host_mirror_compiles_and_runs(tmp_path):
     assert "FAIL" not in out
 
 
+def test_cpp_host_mirror_binds_every_export():
+    """like tests/test_rust_ffi.py for the Rust crate: the C++ mirror wraps every entry point the header declares
+    (the ode_b200_debug_* test hooks aside), so a new export cannot be forgotten on the compiled-host side"""
+    import re
+    hpp = open(os.path.join(LIBDIR, "cpp", "ode_b200.hpp")).read()
+    missing = [sym for sym in _abi.ABI_SYMBOLS if "_debug_" not in sym and not re.search(r"\b%s\(" % sym, hpp)]
+    assert not missing, missing
+
+
 @pytest.mark.gpu
 def test_cpp_host_mirror_on_gpu(tmp_path):
     exe = str(tmp_path / "cpp_host_smoke")
     out = _build_and_run(tmp_path, [GXX, "-std=c++17", "-I", os.path.join(ROOT, "include"), "-I",
                                     os.path.join(LIBDIR, "cpp"), os.path.join(ROOT, "tests", "cpp_host_smoke.cpp"),
                                     "-L", LIBDIR, "-lode_b200", "-o", exe], exe)
-    assert "dopri5 test1" in out and "FAIL" not in out and out.count("ok") >= 3
+    assert "dopri5 test1" in out and "FAIL" not in out and out.count(": ok") >= 15 and "0 checks failed" in out
 
 
 def test_save_formats_like_rust_display(tmp_path):

@@ -10,6 +10,8 @@ timeout 600 bash tools/ncu_capture.sh bench_lorenz_dopri5_2p20 lorenz_dp5 104857
 timeout 900 bash tools/ncu_capture.sh bench_kepler_dop853_2p22 kepler_dp8 4194304 $J > $O/ev_c2.log 2>&1
 timeout 600 bash tools/ncu_capture.sh split_threebody18_dop853_sparse_2p18 threebody18_dp8 262144 $J > $O/ev_c3.log 2>&1
 timeout 600 bash tools/ncu_capture.sh split_threebody18_dop853_cont8_2p18 threebody18_dp8_com 262144 $J > $O/ev_c4.log 2>&1
+timeout 600 bash tools/ncu_capture.sh split_threebody18_dopri5_sparse_2p18 threebody18_dp5 262144 $J > $O/ev_c4a.log 2>&1
+timeout 600 bash tools/ncu_capture.sh split_threebody18_dopri5_cont_2p18 threebody18_dp5_com 262144 $J > $O/ev_c4b.log 2>&1
 timeout 600 bash tools/ncu_capture.sh kepler_dopri5_2p20 kepler_dp5 1048576 $J > $O/ev_c5.log 2>&1
 timeout 600 bash tools/ncu_capture.sh lorenz_rk4_all_steps_2p18 lorenz_rk4_all_steps 262144 $J > $O/ev_c6.log 2>&1
 timeout 600 bash tools/ncu_capture.sh lorenz_dopri5_dense_2001_2p18 lorenz_dp5_dense_hbm 262144 $J > $O/ev_c7.log 2>&1
