@@ -290,6 +290,8 @@ def load():
     lib.ode_b200_tableau.restype = C.c_double
     lib.ode_b200_debug_pow.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ode_b200_debug_pow.restype = C.c_int
+    lib.ode_b200_debug_powf.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ode_b200_debug_powf.restype = C.c_int
     lib.ode_b200_debug_exp.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     lib.ode_b200_debug_exp.restype = C.c_int
     lib.ode_b200_debug_div.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]

@@ -82,3 +82,38 @@ def test_product_package_never_imports_the_oracle():
                 txt = open(os.path.join(dp, f), errors="replace").read()
                 assert "libode_oracle" not in txt and "import oracle" not in txt, os.path.join(dp, f)
                 assert "ode_oracle_" not in txt or f == "ode_systems.cuh", os.path.join(dp, f)
+
+
+def test_ctypes_prototypes_match_the_header():
+    """every argtypes / restype the Python wrapper (and tests/oracle.py through it) declares agrees with the C
+    prototype in include/ode_b200.h: argument count, integer width, float vs double, pointer vs scalar. A wrong width
+    would silently truncate an argument on both sides of a parity test."""
+    import ctypes as C
+    from test_rust_ffi import c_protos
+    lib = _abi.load()
+    scalar = {"c_int": (C.c_int,), "i32": (C.c_int32, C.c_int), "u32": (C.c_uint32, C.c_uint), "i64": (C.c_int64, C.c_longlong, C.c_long),
+              "u64": (C.c_uint64, C.c_ulonglong, C.c_ulong), "c_double": (C.c_double,), "c_float": (C.c_float,), "u8": (C.c_uint8,)}
+
+    def is_pointer(t):
+        return t in (C.c_void_p, C.c_char_p) or (isinstance(t, type) and issubclass(t, C._Pointer))
+
+    checked = 0
+    for name, (ret, args) in c_protos().items():
+        fn = getattr(lib, name)
+        if fn.argtypes is None:
+            assert not args, "%s takes %d arguments but declares no argtypes" % (name, len(args))
+        else:
+            assert len(fn.argtypes) == len(args), (name, len(fn.argtypes), args)
+            for i, (ct, want) in enumerate(zip(fn.argtypes, args)):
+                if want.startswith("*"):
+                    assert is_pointer(ct), (name, i, ct, want)
+                else:
+                    assert ct in scalar[want], (name, i, ct, want)
+        if ret is None:
+            assert fn.restype is None, name
+        elif ret.startswith("*"):
+            assert is_pointer(fn.restype), (name, fn.restype, ret)
+        else:
+            assert fn.restype in scalar[ret], (name, fn.restype, ret)
+        checked += 1
+    assert checked == len(_abi.ABI_SYMBOLS)
