@@ -427,7 +427,8 @@ class ContinuousOutputModel:
 
     def add_interval(self, breakpoint, coefficients, step_size):
         self.breakpoints.append(float(breakpoint))
-        self.intervals.append(Interval([np.asarray(c, dtype=np.float64) for c in coefficients], float(step_size)))
+        dt = np.float32 if all(getattr(c, "dtype", None) == np.float32 for c in coefficients) else np.float64
+        self.intervals.append(Interval([np.asarray(c, dtype=dt) for c in coefficients], float(step_size)))
 
     def bounds(self):
         return self.lower_bound, self.breakpoints[-1]
@@ -438,6 +439,8 @@ class ContinuousOutputModel:
         m = len(self.intervals[0].coefficients)
         if m == 0:
             raise IndexError("interval without coefficients")
+        if self.intervals[0].coefficients[0].dtype == np.float32:
+            return self._evaluate_f32(np.float32(x))
         dim = self.intervals[0].coefficients[0].size
         k = len(self.intervals)
         out = _abi.HostOutputs(1, dim, 0, k, m)
@@ -449,6 +452,26 @@ class ContinuousOutputModel:
         out.com_count[0] = k
         y, found = com_evaluate_batch(out, [x], ctx)
         return y[0, 0].copy() if found[0, 0] else None
+
+    def _evaluate_f32(self, x):
+        """continuous_output_model.rs:31-56,86-104 with T = f32 on the host (the device kernel is f64): every
+        operation on np.float32 values, one rounding each"""
+        import bisect
+        f = np.float32
+        if x < f(self.lower_bound) or x != x:
+            return None
+        idx = bisect.bisect_left([f(b) for b in self.breakpoints], x)
+        if idx >= len(self.intervals):
+            return None
+        lower = f(self.lower_bound) if idx == 0 else f(self.breakpoints[idx - 1])
+        iv = self.intervals[idx]
+        theta = (x - lower) / f(iv.step_size)
+        theta1 = f(1.0) - theta
+        c = iv.coefficients
+        r = c[-1].copy()
+        for i in range(len(c) - 2, -1, -1):
+            r = c[i] + r * (theta if i % 2 == 0 else theta1)
+        return r
 
     def to_dict(self):
         return {"lower_bound": self.lower_bound, "breakpoints": list(self.breakpoints),
@@ -495,7 +518,9 @@ class _Stepper:
     method = None
 
     def __init__(self, f, cfg, y):
-        self.y0 = np.asarray(y, dtype=np.float64).reshape(-1)
+        # T = f32 (`impl FloatNumber for f32`, dop_shared.rs:74): the constructors' dtype=np.float32
+        self.f32 = isinstance(cfg, _abi.ConfigF32)
+        self.y0 = np.asarray(y, dtype=np.float32 if self.f32 else np.float64).reshape(-1)
         if isinstance(f, DynSystem):  # DVector state: its length is the dimension
             f = f.resolve(self.y0.size)
         self.f, self.cfg = f, cfg
@@ -517,8 +542,8 @@ class _Stepper:
         cap = self._guess_cap()
         want_com = com is not None
         while True:
-            out = integrate_batch(self.f, self.cfg, self.y0.reshape(-1, 1), out_cap=cap,
-                                  com_cap=cap if want_com else 0, ctx=ctx)
+            out = (integrate_batch_f32 if self.f32 else integrate_batch)(
+                self.f, self.cfg, self.y0.reshape(-1, 1), out_cap=cap, com_cap=cap if want_com else 0, ctx=ctx)
             need = int(out.out_count[0])
             need_com = int(out.com_count[0]) if want_com else 0
             if need <= cap and need_com <= cap:
@@ -556,14 +581,16 @@ class Dopri5(_Stepper):
     """src/dopri5.rs"""
 
     @classmethod
-    def new(cls, f, x, x_end, dx, y, rtol, atol):
-        return cls(f, config_new(_abi.DOPRI5, x, x_end, dx, rtol, atol), y)
+    def new(cls, f, x, x_end, dx, y, rtol, atol, dtype=np.float64):
+        mk = config_new_f32 if np.dtype(dtype) == np.float32 else config_new
+        return cls(f, mk(_abi.DOPRI5, x, x_end, dx, rtol, atol), y)
 
     @classmethod
     def from_param(cls, f, x, x_end, dx, y, rtol, atol, safety_factor, beta, fac_min, fac_max, h_max, h, n_max,
-                   n_stiff, out_type):
-        return cls(f, config_from_param(_abi.DOPRI5, x, x_end, dx, rtol, atol, safety_factor, beta, fac_min,
-                                        fac_max, h_max, h, n_max, n_stiff, out_type), y)
+                   n_stiff, out_type, dtype=np.float64):
+        mk = config_from_param_f32 if np.dtype(dtype) == np.float32 else config_from_param
+        return cls(f, mk(_abi.DOPRI5, x, x_end, dx, rtol, atol, safety_factor, beta, fac_min,
+                         fac_max, h_max, h, n_max, n_stiff, out_type), y)
 
     def integrate(self, ctx=None):
         if self.cfg.out_type == _abi.OUT_CONTINUOUS:  # dopri5.rs:256-258 panics
@@ -580,14 +607,16 @@ class Dop853(_Stepper):
     """src/dop853.rs (no ContinuousOutputModel support, as in the reference)"""
 
     @classmethod
-    def new(cls, f, x, x_end, dx, y, rtol, atol):
-        return cls(f, config_new(_abi.DOP853, x, x_end, dx, rtol, atol), y)
+    def new(cls, f, x, x_end, dx, y, rtol, atol, dtype=np.float64):
+        mk = config_new_f32 if np.dtype(dtype) == np.float32 else config_new
+        return cls(f, mk(_abi.DOP853, x, x_end, dx, rtol, atol), y)
 
     @classmethod
     def from_param(cls, f, x, x_end, dx, y, rtol, atol, safety_factor, beta, fac_min, fac_max, h_max, h, n_max,
-                   n_stiff, out_type):
-        return cls(f, config_from_param(_abi.DOP853, x, x_end, dx, rtol, atol, safety_factor, beta, fac_min,
-                                        fac_max, h_max, h, n_max, n_stiff, out_type), y)
+                   n_stiff, out_type, dtype=np.float64):
+        mk = config_from_param_f32 if np.dtype(dtype) == np.float32 else config_from_param
+        return cls(f, mk(_abi.DOP853, x, x_end, dx, rtol, atol, safety_factor, beta, fac_min,
+                         fac_max, h_max, h, n_max, n_stiff, out_type), y)
 
     def integrate(self, ctx=None):
         return self._run(ctx=ctx)
@@ -595,6 +624,8 @@ class Dop853(_Stepper):
     def integrate_with_continuous_output_model(self, continuous_output, ctx=None):
         """EXTENSION (the reference has this for Dopri5 only): record Dop853's 8 dense-output
         vectors per accepted step as model intervals (ODE_B200_OUT_CONTINUOUS8)."""
+        if self.f32:
+            raise ValueError("the Continuous8 extension exists for f64 only")
         self.cfg.out_type = _abi.OUT_CONTINUOUS8
         return self._run(com=continuous_output, ctx=ctx)
 
@@ -603,8 +634,8 @@ class Rk4(_Stepper):
     """src/rk4.rs -- note the argument order (f, x, y, x_end, step_size)"""
 
     @classmethod
-    def new(cls, f, x, y, x_end, step_size):
-        return cls(f, config_rk4(x, x_end, step_size), y)
+    def new(cls, f, x, y, x_end, step_size, dtype=np.float64):
+        return cls(f, (config_rk4_f32 if np.dtype(dtype) == np.float32 else config_rk4)(x, x_end, step_size), y)
 
     def integrate(self, ctx=None):
         return self._run(ctx=ctx)

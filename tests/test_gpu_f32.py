@@ -187,3 +187,35 @@ def test_f32_adaptive_random_configurations_bitwise(seed):
     cap = int(rng.choice([0, 5, 60, 400]))
     com = int(rng.choice([0, 7, 400])) if (out_type == ob.OUT_CONTINUOUS and method == ob.DOPRI5) else 0
     check_adaptive(system, cfg, y0, p, cap, com, "f32 fuzz %d" % seed)
+
+
+def test_f32_stepper_classes_mirror_the_crate():
+    """the host mirror's Rk4 / Dopri5 / Dop853 with dtype=np.float32 (Rk4::<f32>, Dopri5::<f32>: bouncing_ball.rs:15,
+    35-36) return what the batched f32 entry returns for the same trajectory, x_out()/y_out() in f32"""
+    f = ob.System.builtin("bouncing_ball", [9.81])
+    r = ob.Rk4.new(f, 0.0, [10.0, 0.0, 0.0], 10.0, 0.01, dtype=np.float32)
+    st = r.integrate()
+    g = ob.rk4_f32_integrate_batch(f, 0.0, 10.0, 0.01, np.array([[10.0], [0.0], [0.0]]), out_cap=1100)
+    n = int(g.out_count[0])
+    assert st.accepted_steps == g.accepted[0] == 143 and len(r.x_out()) == n
+    assert same_f32(np.array(r.y_out()), g.out_y[0, :n]).all() and r.y_out()[0].dtype == np.float32
+    d = ob.Dopri5.new(f, 0.0, 10.0, 0.01, [10.0, 0.0, 0.0], 1e-2, 1e-6, dtype=np.float32)
+    st = d.integrate()
+    cfg = ob.config_new_f32(ob.DOPRI5, 0.0, 10.0, 0.01, 1e-2, 1e-6)
+    g = ob.integrate_batch_f32(f, cfg, np.array([[10.0], [0.0], [0.0]]), out_cap=1100)
+    n = int(g.out_count[0])
+    assert (st.num_eval, st.accepted_steps, st.rejected_steps) == (g.num_eval[0], g.accepted[0], g.rejected[0])
+    assert same_f32(np.array(d.y_out()), g.out_y[0, :n]).all() and same_f32(np.array(d.x_out()), g.out_x[0, :n]).all()
+    com = ob.ContinuousOutputModel()
+    c = ob.Dopri5.new(ob.System.builtin("lorenz", [10.0, 8.0 / 3.0, 28.0]), 0.0, 1.0, 0.1, [1.0, 1.0, 1.0], 1e-4, 1e-4,
+                      dtype=np.float32)
+    st = c.integrate_with_continuous_output_model(com)
+    assert len(com.intervals) == st.accepted_steps and com.intervals[0].coefficients[0].dtype == np.float32
+    y = com.evaluate(0.5)
+    assert y is not None and np.all(np.isfinite(y)) and com.evaluate(1.5) is None
+    e = ob.Dop853.from_param(ob.System.builtin("lorenz", [10.0, 8.0 / 3.0, 28.0]), 0.0, 1.0, 0.1, [1.0, 1.0, 1.0], 1e-4, 1e-4,
+                             0.9, 0.0, 0.333, 6.0, 1.0, 0.0, 100000, 1000, ob.OutputType.Sparse, dtype=np.float32)
+    st = e.integrate()
+    assert st.accepted_steps > 3 and abs(e.x_out()[-1] - 1.0) < 1e-6
+    with pytest.raises(ValueError):
+        e.integrate_with_continuous_output_model(ob.ContinuousOutputModel())
