@@ -496,6 +496,8 @@ def run_native(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     lib = _abi.load()
+    if args.no_pipeline:  # profiler runs only: ncu serialises kernels and cannot profile one that waits for host copies
+        os.environ["ODE_B200_PIPELINE"] = "0"  # read by every context the library creates (the multi-GPU entry's too)
     ctx = ob.Context(local)
     # The host-buffer entry runs its default transfer mode: the chunked upload / integrate / copy-back pipeline
     # (include/ode_b200.h, ode_b200_set_pipeline): the kernel starts before its inputs have arrived and finished
@@ -648,6 +650,9 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the other_workloads leg")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="e2e leg without the upload / integrate / copy-back pipeline (for runs under ncu, which "
+                         "serialises kernels and cannot profile one that waits for concurrent host copies)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

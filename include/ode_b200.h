@@ -307,6 +307,9 @@ int ode_b200_set_work_queue(ode_b200_ctx* ctx, int enabled);
  * pinned host memory (cudaHostAlloc / cudaHostRegister); 0 switches it off
  * (upload, kernel, copy-back one after the other, or zero-copy result stores: ode_b200_set_zero_copy). */
 int ode_b200_set_pipeline(ode_b200_ctx* ctx, int chunk_log2);
+/* The environment variable ODE_B200_PIPELINE=<chunk_log2> sets the initial value for every context of the process
+ * (incl. the ones ode_b200_integrate_batch_multi creates): ODE_B200_PIPELINE=0 for runs under a profiler that
+ * serialises kernels (ncu), which cannot execute a kernel that waits for concurrent host copies. */
 /* large states: 1 (default) = Dopri5 and Dop853 run one trajectory per group of three lanes for the systems that
  * have that form (threebody18), the state and stage vectors dealt out component-wise so that they stay in
  * registers; 0 = one trajectory per thread like everything else (kept for the ablation; same bits) */

@@ -271,6 +271,13 @@ extern "C" ode_b200_ctx* ode_b200_create(int device) {
     }
     ode_b200_ctx* c = new ode_b200_ctx();
     c->device = device;
+    /* ODE_B200_PIPELINE=<chunk_log2>: initial value of ode_b200_set_pipeline for every context of the process, also
+     * the ones ode_b200_integrate_batch_multi makes (0 = off: a profiler that serialises kernels cannot run one
+     * that waits for concurrent host copies) */
+    if (const char* e = getenv("ODE_B200_PIPELINE")) {
+        const int v = atoi(e);
+        if (v == 0 || (v >= 8 && v <= 24)) c->pipeline_shift = v;
+    }
     bool ok = cudaSetDevice(device) == cudaSuccess &&
               cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess &&
               cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&

@@ -13,7 +13,17 @@ static void report(const char* what, bool ok) {
     if (!ok) ++fails;
 }
 
+static int run();
 int main() {
+    try {
+        return run();
+    } catch (const std::exception& e) {
+        std::printf("exception: %s -> FAIL\n", e.what());
+        return 1;
+    }
+}
+
+static int run() {
     // host-only parts of the surface
     report("abi version", abi_version() == ODE_B200_ABI_VERSION);
     report("tableau c5[1] = 1/5", tableau("c5", 1) == 1.0 / 5.0);
@@ -73,10 +83,10 @@ int main() {
         for (int j = 0; j < 6; ++j) same = same && kd.y_out()[i][j] == ks.y_out()[i][j];
     report("DVector == SVector (Kepler, Dop853 dense)", same);
     // f32 (examples/bouncing_ball.rs:15,35-36): Rk4::<f32> stops at the ground through solout; Dopri5::<f32> runs
-    auto b = Rk4<2, float>::new_(System::builtin("bouncing_ball"), 0.0f, {10.0f, 0.0f}, 10.0f, 0.01f);
+    auto b = Rk4<3, float>::new_(System::builtin("bouncing_ball", {9.81}), 0.0f, {10.0f, 0.0f, 0.0f}, 10.0f, 0.01f);
     b.integrate(ctx);
     report("rk4 f32 bouncing ball", !b.y_out().empty() && b.y_out().back()[0] < 0.0f && b.x_out().back() < 2.0f);
-    auto b5 = Dopri5<2, float>::new_(System::builtin("bouncing_ball"), 0.0f, 10.0f, 0.01f, {10.0f, 0.0f}, 1e-4f, 1e-6f);
+    auto b5 = Dopri5<3, float>::new_(System::builtin("bouncing_ball", {9.81}), 0.0f, 10.0f, 0.01f, {10.0f, 0.0f, 0.0f}, 1e-2f, 1e-6f);
     Stats s5 = b5.integrate(ctx);
     report("dopri5 f32 bouncing ball", s5.accepted_steps > 0 && !b5.y_out().empty());
     // batched call + knobs: 1000 Lorenz trajectories, with and without the work queue -> identical results

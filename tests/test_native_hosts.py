@@ -18,7 +18,9 @@ def _build_and_run(tmp_path, cmd, exe):
     _abi.load()
     subprocess.run(cmd, check=True)
     env = dict(os.environ, LD_LIBRARY_PATH=LIBDIR + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
-    return subprocess.run([exe], check=True, capture_output=True, text=True, env=env).stdout
+    r = subprocess.run([exe], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return r.stdout
 
 
 def test_c_header_links_and_struct_layout(tmp_path):

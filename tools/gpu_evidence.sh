@@ -24,5 +24,5 @@ cp $J profiles/r2_ncu_summaries.json
 timeout 900 python bench.py > $O/bench_ev_n1.json 2> $O/bench_ev_n1.err; echo "bench rc=$?" >> $O/bench_ev_n1.err; tail -n 3 $O/bench_ev_n1.err
 timeout 600 python bench.py --impl reference > $O/bench_ev_ref.json 2> $O/bench_ev_ref.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/ev_launches.csv \
-   python bench.py --steps 2 --warmup 3 --no-cpu --no-extra > $O/ev_ncu_bench.log 2>&1
+   python bench.py --steps 2 --warmup 3 --no-cpu --no-extra --no-pipeline > $O/ev_ncu_bench.log 2>&1
 cat $O/ev_com.log; ls -la $O | head -40
