@@ -63,11 +63,14 @@ static int run() {
     auto vh = com.evaluate_host(3.0);
     report("dopri5 continuous model", v && std::fabs((*v)[0] + std::log(28.0)) < 1e-9 && !com.evaluate(ctx, 6.0001) && vh &&
                                           std::fabs((*vh)[0] - (*v)[0]) < 1e-15);
-    ContinuousOutputModel<State<1>> com8;
-    auto c8 = Dop853<1>::new_(System::builtin("test_cubic"), 0.0, 6.0, 0.1, {0.0}, 1e-10, 1e-10);
+    ContinuousOutputModel<State<3>> com8;
+    auto c8 = Dop853<3>::new_(sys, 0.0, 1.0, 0.1, {1.0, 1.0, 1.0}, 1e-9, 1e-9);
     c8.integrate_with_continuous_output_model(ctx, com8);
-    auto v8 = com8.evaluate(ctx, 3.0);
-    report("dop853 continuous model", v8 && std::fabs((*v8)[0] + std::log(28.0)) < 1e-9 && com8.intervals[0].coefficients.size() == 8);
+    auto d8 = Dop853<3>::new_(sys, 0.0, 1.0, 0.1, {1.0, 1.0, 1.0}, 1e-9, 1e-9);  // Dense: samples at 0, 0.1, ..., 1.0
+    d8.integrate(ctx);
+    auto v8 = com8.evaluate(ctx, d8.x_out()[5]);
+    report("dop853 continuous model", v8 && d8.y_out().size() == 11 && std::fabs((*v8)[0] - d8.y_out()[5][0]) < 1e-12 &&
+                                          com8.intervals[0].coefficients.size() == 8 && !com8.evaluate(ctx, 1.5));
     // the *_dvector.rs examples: run-time state dimension, same bits as the SVector form
     auto kd = Dop853Dyn::new_(System::builtin("kepler", {398600.435436}), 0.0, 3600.0, 60.0,
                               DState<>{-5007.248417988539, -1444.918140151374, 3628.534606178356, 0.717716656891, -10.224093784269,
