@@ -7,6 +7,7 @@
  * No CPU fallback exists anywhere in this file: without a usable CUDA device every
  * integrate entry point returns an error.
  */
+#include <cuda.h> /* types of the tensor-map encoder only: the entry point comes from cudaGetDriverEntryPoint */
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -233,6 +234,7 @@ struct ode_b200_ctx {
     int use_queue = 1;
     int zero_copy = 1; /* per-trajectory results straight into pinned host arrays (ode_b200_set_zero_copy) */
     int lane_split = 1; /* large states: one trajectory per group of three lanes where the system has that form */
+    int tensor_stores = 1; /* Rk4 STAGE kernels: one TMA tensor store per warp and group of samples (ODE_B200_TENSOR_STORES=0: off) */
     /* host pipeline of the host-buffer entry (ode_kernel_args.h): log2 of the chunk size, 0 = off */
     int pipeline_shift = 16;
     cudaStream_t up_stream = nullptr, copy_stream = nullptr;
@@ -274,6 +276,7 @@ extern "C" ode_b200_ctx* ode_b200_create(int device) {
     /* ODE_B200_PIPELINE=<chunk_log2>: initial value of ode_b200_set_pipeline for every context of the process, also
      * the ones ode_b200_integrate_batch_multi makes (0 = off: a profiler that serialises kernels cannot run one
      * that waits for concurrent host copies) */
+    if (const char* e = getenv("ODE_B200_TENSOR_STORES")) c->tensor_stores = atoi(e) != 0; /* ablation switch */
     if (const char* e = getenv("ODE_B200_PIPELINE")) {
         const int v = atoi(e);
         if (v == 0 || (v >= 8 && v <= 24)) c->pipeline_shift = v;
@@ -399,6 +402,39 @@ struct PipeArgs { /* host pipeline of this launch (ode_kernel_args.h); shift == 
     unsigned* chunk_flag = nullptr;
 };
 
+/* Tensor maps of the Rk4 STAGE kernels' warp-level result stores (KernelArgs::map_y / map_x, push_warp_):
+ * out_y as [n_traj][out_pitch / G][G * dim] doubles and out_x as [n_traj][out_pitch / G][G], box = 32 trajectories x
+ * 1 group. Returns 1 when both are set. */
+static int make_result_maps(KernelArgs* ka, int dim) {
+    typedef CUresult (*encode_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_t encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            fn = nullptr;
+        (void)cudaGetLastError();
+        return (encode_t)fn;
+    }();
+    const int G = stage_group(dim, ODE_B200_RK4);
+    if (!encode || ka->out_pitch % G != 0 || ka->n_traj > 0x7fffffffLL || ka->out_pitch / G > 0x7fffffffLL) return 0;
+    static_assert(sizeof(CUtensorMap) == sizeof(TensorMapBlob), "CUtensorMap is 128 bytes");
+    auto make = [&](double* base, int inner, TensorMapBlob* out) {
+        CUtensorMap m;
+        const cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)(ka->out_pitch / G), (cuuint64_t)ka->n_traj};
+        const cuuint64_t strides[2] = {(cuuint64_t)inner * 8, (cuuint64_t)(ka->out_pitch / G) * inner * 8};
+        const cuuint32_t box[3] = {(cuuint32_t)inner, 1, 32}, es[3] = {1, 1, 1};
+        if (encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+        memcpy(out, &m, sizeof(m));
+        return true;
+    };
+    return make(ka->out.out_y, G * dim, &ka->map_y) && make(ka->out.out_x, G, &ka->map_x) ? 1 : 0;
+}
+
 static int launch_device(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg, int64_t n, const double* y0,
                          const double* params, int per_traj, const ode_b200_outputs* out, long long out_pitch,
                          long long com_pitch, cudaStream_t stream, const PipeArgs* pipe = nullptr) {
@@ -497,6 +533,8 @@ static int launch_device(ode_b200_ctx* c, int sys_id, const ode_b200_config* cfg
         split_fn = split->fn[1][cfg->out_type];
         dyn_smem = (size_t)(block / 32) * kBuiltins[sys_id]->split_traj_per_warp * split->slot_bytes;
     }
+    ka.tensor_out = 0;
+    if (stage && cfg->method == ODE_B200_RK4 && c->tensor_stores) ka.tensor_out = make_result_maps(&ka, s.dim);
     CUDA_TRY(cudaMemsetAsync(ka.queue, 0, sizeof(unsigned long long), stream));
     if (stream == c->stream) CUDA_TRY(cudaEventRecord(c->ev0, stream));
     if (!s.jit) {

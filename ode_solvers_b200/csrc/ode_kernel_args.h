@@ -52,6 +52,9 @@ __host__ __device__ constexpr bool records_dense(int method, int out_type) {
  * 16-byte aligned range of the trajectory's slice of out_y), writes its x values with two 16-byte
  * stores, and goes on filling the other group -- no warp-level flush in the step loop. tools/micro/bulk_store.cu: 3.5-4.0 TB/s for this pattern on B200 (32 B + 96 B copies),
  * 4.3-4.6 TB/s with whole 8-sample runs, against 1.1-1.4 TB/s for per-lane vector stores.
+ * Rk4 (all lanes of a warp record the same steps) goes one step further: the groups of a warp's 32 lanes leave as
+ * ONE TMA tensor store per array (KernelArgs::map_y / map_x, push_warp_ in ode_device.cuh): 4.4-4.7 TB/s in the
+ * micro-benchmark, 4.59 -> 4.15 ms for 2^18 Lorenz trajectories x 2001 recorded steps.
  * It needs an even row pitch (alignment) and shared memory, so the launcher picks it only for
  * output-heavy calls (rule in ode_b200.cu). Lane buffer: x[R] then y[R][dim], R = 2 groups.
  */
@@ -82,6 +85,11 @@ __host__ __device__ constexpr int com_stage_stride(int dim, int m, int threads) 
 __host__ __device__ constexpr int stage_smem_doubles(int dim, int threads, int m, int method = ODE_B200_DOPRI5) {
     return threads * (stage_stride(dim, method) + (m > 0 ? com_stage_stride(dim, m, threads) : 0));
 }
+
+/* a CUtensorMap (128 bytes, 64-byte aligned) without <cuda.h>: the kernels only pass its address to the TMA engine */
+struct alignas(64) TensorMapBlob {
+    unsigned long long w[16];
+};
 
 struct KernelArgs {
     ode_b200_config cfg;        /* batch-uniform solver parameters (from_param argument list) */
@@ -115,6 +123,14 @@ struct KernelArgs {
     const unsigned* upload_ready;
     unsigned* chunk_done;
     unsigned* chunk_flag;
+    /* Warp-level result stores of the Rk4 STAGE kernels (ode_device.cuh, push_warp_): when the 32 lanes of a warp
+     * hold 32 consecutive trajectories and record the same steps (Rk4 without solout: always, except in the last,
+     * partial warp of a batch), a finished group of samples of ALL its lanes leaves as ONE TMA tensor store per
+     * array -- box = 32 trajectories x 1 group, rows a trajectory pitch apart -- instead of one bulk copy per lane.
+     * map_y: out_y as [n_traj][out_pitch / G][G * dim] doubles, map_x: out_x as [n_traj][out_pitch / G][G];
+     * tensor_out = 0: maps not set (row pitch not a multiple of the group, driver without the entry point). */
+    int tensor_out;
+    TensorMapBlob map_y, map_x;
 };
 
 /* the f32 kernels' arguments (device pointers) */

@@ -100,6 +100,9 @@ struct Rk4Stepper {
     static constexpr bool kLockstep = lockstep_for(N, ODE_B200_RK4);
     static constexpr int kThreads = block_threads_for(N, ODE_B200_RK4, false);
     static constexpr int kRefillIdle = kLockstep ? ODE_B200_REFILL_IDLE : ODE_B200_REFILL_IDLE_FREE;
+    /* every lane of a warp records the same steps (no solout): a warp of 32 consecutive trajectories hands its
+     * samples to the TMA engine with ONE tensor store per group and array (push_warp_, ode_device.cuh) */
+    static constexpr bool kTensorOut = STAGE && !Sys::HAS_SOLOUT;
     struct State {
         double y[N];
         double p[Sys::NP > 0 ? Sys::NP : 1];
@@ -108,7 +111,28 @@ struct Rk4Stepper {
         Counters c;
         long long traj;
         int status;
+        bool uni; /* kTensorOut: set by the lane scheduler for a full warp of consecutive trajectories (warp-uniform) */
     };
+
+    ODE_DEV static void push(const KernelArgs& a, State& s, double x, const double (&y)[N]) {
+        if constexpr (kTensorOut) {
+            if (s.uni) {
+                push_warp_<N, ODE_B200_RK4>(a, s.traj, s.c, x, y);
+                return;
+            }
+        }
+        push_<N, STAGE, 0, ODE_B200_RK4>(a, s.traj, s.c, x, y);
+    }
+    ODE_DEV static void finish(const KernelArgs& a, State& s, double step) {
+        if constexpr (kTensorOut) {
+            if (s.uni) {
+                flush_warp_tail_<N, ODE_B200_RK4>(a, s.traj, s.c);
+                store_final_<N, false, 1, 0, ODE_B200_RK4>(a, s.traj, s.y, s.x, step, s.c, s.status, 0.0);
+                return;
+            }
+        }
+        store_final_<N, STAGE, 1, 0, ODE_B200_RK4>(a, s.traj, s.y, s.x, step, s.c, s.status, 0.0);
+    }
 
     /* Rk4::integrate prologue, rk4.rs:71-77 */
     ODE_DEV static void init(State& s, const KernelArgs& a, long long t) {
@@ -117,7 +141,8 @@ struct Rk4Stepper {
         s.x = a.cfg.x0;
         counters_init_<STAGE>(s.c);
         s.status = ODE_B200_OK;
-        push_<N, STAGE, 0, ODE_B200_RK4>(a, t, s.c, s.x, s.y);
+        if constexpr (!kTensorOut) s.uni = false;
+        push(a, s, s.x, s.y);
         const double ns = ceil((a.cfg.x_end - s.x) / a.cfg.step_size);
         if (!(ns >= 0.0) || ns > 4.0e9) { /* to_usize().unwrap() panics in the reference */
             s.status = ODE_B200_UNSUPPORTED_DOMAIN;
@@ -163,7 +188,7 @@ struct Rk4Stepper {
     /* one Rk4::step + the loop body of integrate, rk4.rs:79-98,103-132 */
     ODE_DEV static bool attempt(State& s, const KernelArgs& a) {
         if (s.steps_left == 0) {
-            store_final_<N, STAGE, 1, 0, ODE_B200_RK4>(a, s.traj, s.y, s.x, a.cfg.step_size, s.c, s.status, 0.0);
+            finish(a, s, a.cfg.step_size);
             return true;
         }
         const double step = a.cfg.step_size, x = s.x;
@@ -193,14 +218,14 @@ struct Rk4Stepper {
         s.x = x_new;
 #pragma unroll
         for (int i = 0; i < N; ++i) s.y[i] = w.yn[i];
-        push_<N, STAGE, 0, ODE_B200_RK4>(a, s.traj, s.c, x_new, w.yn);
+        push(a, s, x_new, w.yn);
         s.c.num_eval += 4;
         s.c.accepted += 1;
         s.c.n_step += 1;
         s.steps_left -= 1;
         if (stop) s.steps_left = 0;
         if (s.steps_left == 0) {
-            store_final_<N, STAGE, 1, 0, ODE_B200_RK4>(a, s.traj, s.y, s.x, step, s.c, s.status, 0.0);
+            finish(a, s, step);
             return true;
         }
         return false;

@@ -230,3 +230,29 @@ def test_trajectories_that_end_in_the_pass_they_were_claimed_in(system):
             ctx.close()
             assert (g.status == want).all(), "%d trajectories were never integrated" % int((g.status == -1).sum())
             assert (g.y_final == y0).all() and (g.accepted == 0).all()
+
+
+@pytest.mark.parametrize("n,cap,steps", [(32, 8, 7), (33, 7, 9), (31, 4, 3), (64, 5, 12), (4096 + 5, 13, 12), (4096, 16, 15),
+                                         (2 * 148 * 640 + 77, 6, 5), (1000, 3, 0)])
+def test_rk4_warp_level_result_stores(n, cap, steps, monkeypatch):
+    """Rk4 with every step recorded: full warps of consecutive trajectories hand their samples to the TMA engine as
+    one tensor store per group (push_warp_), partial warps through per-lane bulk copies -- capacities that are no
+    multiple of the group, that cut the run short (the counts go on), several generations per lane, zero steps,
+    both schedules, and the switch off: identical bits"""
+    import oracle
+    y0, p = W.lorenz_ensemble(n, offset=17)
+    cfg = ob.config_rk4(0.0, steps * 1e-3, 1e-3)
+    sel = np.arange(n) if n <= 5000 else np.concatenate([np.arange(0, 700), np.arange(n - 700, n), np.arange(0, n, 389)])
+    o = oracle.integrate_batch("lorenz", cfg, y0[:, sel], p, out_cap=cap)
+    for tensor in ("1", "0"):
+        monkeypatch.setenv("ODE_B200_TENSOR_STORES", tensor)
+        for queue in (True, False):
+            ctx = ob.Context(0)
+            ctx.set_work_queue(queue)
+            g = ob.integrate_batch(ob.System.builtin("lorenz"), cfg, y0, p, out_cap=cap, ctx=ctx)
+            ctx.close()
+            assert (g.out_count == steps + 1).all() and (g.status == (ob.OK if steps + 1 <= cap else ob.OUTPUT_CAPACITY_EXCEEDED)).all()
+            c = min(cap, steps + 1)
+            assert (g.out_x[sel, :c].view(np.uint64) == o.out_x[:, :c].view(np.uint64)).all(), (tensor, queue)
+            assert (g.out_y[sel, :c].view(np.uint64) == o.out_y[:, :c].view(np.uint64)).all(), (tensor, queue)
+            assert (g.y_final[:, sel].view(np.uint64) == o.y_final.view(np.uint64)).all()

@@ -68,6 +68,7 @@ CASES = [
     ("bouncing_ball", W.bouncing_ball_ensemble, ob.DOPRI5, ob.OUT_DENSE, 10.0, None, 1010, 0),  # ragged early stops
     ("threebody18", W.threebody18_ensemble, ob.DOP853, ob.OUT_SPARSE, 1.5, 1e-8, 0, 0),  # three lanes per trajectory
     ("threebody18", W.threebody18_ensemble, ob.DOP853, ob.OUT_CONTINUOUS8, 1.0, 1e-8, 60, 60),
+    ("threebody18", W.threebody18_ensemble, ob.DOPRI5, ob.OUT_SPARSE, 1.5, 1e-7, 0, 0),  # Dopri5 on three lanes
 ]
 
 

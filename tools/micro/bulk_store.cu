@@ -6,8 +6,11 @@
 //   mode 2: per-lane 16-byte vector stores
 //   mode 3: per-lane TMA bulk copies of half runs (R/2 samples: 32 B + 96 B), the other half keeps
 //           filling meanwhile (wait_group.read 1) -- the layout the step-loop kernels use
-// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o bulk_store bulk_store.cu
+//   mode 4: ONE TMA tensor store per warp and half run (lanes in lockstep on consecutive trajectories, the Rk4
+//           case): box = 32 trajectories x (R/2 samples x 3 doubles), rows a trajectory pitch apart
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o bulk_store bulk_store.cu -lcuda
 #include <cstdio>
+#include <cuda.h>
 #include <cuda_runtime.h>
 constexpr int R = 8, N = 3, S = R * (1 + N) + 2;  // lane stride in doubles (16-byte aligned)
 
@@ -15,7 +18,7 @@ __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)_
 
 template <int MODE>
 __global__ void __launch_bounds__(128) k(double* out_x, double* out_y, long long cap, int flushes) {
-    extern __shared__ __align__(16) double buf[];
+    extern __shared__ __align__(128) double buf[];
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double* mine = buf + threadIdx.x * S;
     const unsigned lane = threadIdx.x & 31;
@@ -58,7 +61,7 @@ __global__ void __launch_bounds__(128) k(double* out_x, double* out_y, long long
 
 // half-run groups: slot = sample % R, group g = (sample / (R/2)) % 2; x-run [R] then y-run [R][N]
 __global__ void __launch_bounds__(128) k3(double* out_x, double* out_y, long long cap, int flushes) {
-    extern __shared__ __align__(16) double buf[];
+    extern __shared__ __align__(128) double buf[];
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double* mine = buf + threadIdx.x * S;
     constexpr int G = R / 2;
@@ -78,6 +81,55 @@ __global__ void __launch_bounds__(128) k3(double* out_x, double* out_y, long lon
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// warp-level tensor stores: per warp two group buffers of [32][G*N] (y) and [32][G] (x) doubles, dense
+__global__ void __launch_bounds__(128) k4(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_x,
+                                          int flushes) {
+    extern __shared__ __align__(128) double buf[];
+    constexpr int G = R / 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double* wy = buf + warp * (2 * 32 * G * N + 2 * 32 * G);  // [2][32][G*N] then [2][32][G]
+    double* wx = wy + 2 * 32 * G * N;
+    for (int f = 0; f < 2 * flushes; ++f) {
+        const int g = f & 1;
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        double* my = wy + (g * 32 + lane) * G * N;
+        double* mx = wx + (g * 32 + lane) * G;
+        for (int j = 0; j < G; ++j) {
+            mx[j] = f / 2 + g * G + j;
+            for (int i = 0; i < N; ++i) my[j * N + i] = t + i;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            const int traj0 = (int)(t);  // lane 0's trajectory = the warp's first
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&map_y), "r"(0),
+                         "r"(f), "r"(traj0), "r"(smem_u32(wy + g * 32 * G * N))
+                         : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&map_x), "r"(0),
+                         "r"(f), "r"(traj0), "r"(smem_u32(wx + g * 32 * G))
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+static CUtensorMap make_map(double* base, long long cap, long long nt, int inner) {  // [nt][cap / G][inner] doubles
+    CUtensorMap m;
+    constexpr int G = R / 2;
+    cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)(cap / G), (cuuint64_t)nt};
+    cuuint64_t strides[2] = {(cuuint64_t)inner * 8, (cuuint64_t)(cap / G) * inner * 8};
+    cuuint32_t box[3] = {(cuuint32_t)inner, 1, 32};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = cuTensorMapEncodeTiled(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, es,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) printf("cuTensorMapEncodeTiled failed: %d\n", (int)r);
+    return m;
+}
+
 template <int MODE>
 void run(const char* name, int ctas_per_sm) {
     const int flushes = 250;
@@ -90,12 +142,18 @@ void run(const char* name, int ctas_per_sm) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    const size_t smem = block * S * 8;
+    const size_t smem = MODE == 4 ? (size_t)(block / 32) * (2 * 32 * (R / 2) * (N + 1)) * 8 : block * S * 8;
+    CUtensorMap my, mx;
+    if (MODE == 4) {
+        my = make_map(oy, cap, nt, (R / 2) * N);
+        mx = make_map(ox, cap, nt, R / 2);
+    }
     float best = 1e30f;
     for (int rep = 0; rep < 3; ++rep) {
         cudaEventRecord(e0);
-        if (MODE == 3) k3<<<grid, block, smem>>>(ox, oy, cap, flushes);
-        else k<MODE == 3 ? 0 : MODE><<<grid, block, smem>>>(ox, oy, cap, flushes);
+        if (MODE == 4) k4<<<grid, block, smem>>>(my, mx, flushes);
+        else if (MODE == 3) k3<<<grid, block, smem>>>(ox, oy, cap, flushes);
+        else k<(MODE == 3 || MODE == 4) ? 0 : MODE><<<grid, block, smem>>>(ox, oy, cap, flushes);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms;
@@ -120,6 +178,7 @@ int main() {
         run<1>("warp-cooperative", c);
         run<2>("per-lane 16-byte stores", c);
         run<3>("TMA bulk, half runs", c);
+        run<4>("TMA tensor store per warp", c);
     }
     return 0;
 }
