@@ -240,7 +240,14 @@ struct Dopri5Stepper {
     static constexpr bool DENSE = OUT == ODE_B200_OUT_DENSE;
     static constexpr bool CONT = OUT == ODE_B200_OUT_CONTINUOUS;
     static constexpr bool TRACK_LAST = DENSE && Sys::HAS_SOLOUT;
-    static constexpr int kMinBlocks = min_blocks_for<N, ODE_B200_DOPRI5, DENSE || CONT>();
+    /* the staged Dense kernel (>= 1000 samples per trajectory) runs its sampling loop with rc[5][N], the ring
+     * addresses and the loop state live on top of the step's registers: 3 CTAs x 168 registers beat 4 x 126
+     * (Lorenz, 2001 samples: 17.84 -> 16.00 ms; 2 x 255: 18.07); Continuous and the unstaged kernels do not care */
+#ifdef ODE_B200_MIN_BLOCKS
+    static constexpr int kMinBlocks = ODE_B200_MIN_BLOCKS;
+#else
+    static constexpr int kMinBlocks = (STAGE && DENSE && N <= 4) ? 3 : min_blocks_for<N, ODE_B200_DOPRI5, DENSE || CONT>();
+#endif
     static constexpr bool kSpec = spec_math_for<Sys, ODE_B200_DOPRI5>();
     /* shared-memory ring of ContinuousOutputModel intervals (0: written directly) */
     static constexpr int kCS = (STAGE && CONT) ? com_stage_stride(N, 5, block_threads_for(N, ODE_B200_DOPRI5, true)) : 0;
