@@ -240,9 +240,10 @@ struct Dopri5Stepper {
     static constexpr bool DENSE = OUT == ODE_B200_OUT_DENSE;
     static constexpr bool CONT = OUT == ODE_B200_OUT_CONTINUOUS;
     static constexpr bool TRACK_LAST = DENSE && Sys::HAS_SOLOUT;
-    /* the staged Dense kernel (>= 1000 samples per trajectory) runs its sampling loop with rc[5][N], the ring
-     * addresses and the loop state live on top of the step's registers: 3 CTAs x 168 registers beat 4 x 126
-     * (Lorenz, 2001 samples: 17.84 -> 16.00 ms; 2 x 255: 18.07); Continuous and the unstaged kernels do not care */
+    /* the staged Dense kernel (>= 1000 samples per trajectory): with the bound relaxed from 4 to 3 CTAs per SM ptxas
+     * takes 128 instead of 126 registers (4 CTAs still fit) and stops squeezing the sampling loop: Lorenz, 2001
+     * samples, 17.88 -> 16.01 ms (bound 2: 18.07, bound 5 / 96 registers: 20.45); Continuous and the unstaged
+     * kernels measure the same either way */
 #ifdef ODE_B200_MIN_BLOCKS
     static constexpr int kMinBlocks = ODE_B200_MIN_BLOCKS;
 #else
