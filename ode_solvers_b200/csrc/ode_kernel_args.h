@@ -13,16 +13,26 @@ namespace ode_b200 {
  * 255 registers per thread and CTA-lockstep passes (run_lanes_, ode_device.cuh). Measured on B200:
  * CR3BP/Dop853/Dense 50.7 ms (4 x 128 threads) -> 38.4 (1 x 256) -> 33.5 (lockstep);
  * 3-body-18/Dop853 22.5 -> 16.8 -> 12.5 (128 or 192 threads: 13.2 / 12.8); Kepler/Dopri5 (n = 6, 19 KB
- * of code per pass) gains nothing from it (90.7 against 87.0 ms with 4 x 128 threads).
+ * of code per pass) gains nothing from ONE big CTA (90.7 against 87.0 ms with 4 x 128 threads) -- see below.
  * -DODE_B200_LOCKSTEP=0 switches it off for measurements. */
+/* Dopri5 with n = 6..8 (Kepler, CR3BP: ~19 KB of code per pass, ncu: instruction-cache hit rate 87 %, "no
+ * instruction" 1.0 stalls per issue): lockstep too, but in SMALL CTAs at unchanged occupancy -- 4 CTAs of 128 threads
+ * per SM, each keeping its 4 warps within a pass of each other (round 2, Kepler/Dopri5 2^20: 83.6 ms free-running,
+ * 78.6 with 4 x 128 lockstep, 80.0 with 2 x 256, 83.3 with 1 x 512, 85.7 with 1 x 384 at 168 registers; barrier every
+ * 2 / 4 / 8 passes: 79.6 / 78.6 / 78.7). The n = 3 kernels fit the cache and lose 2 % with it. */
 #ifndef ODE_B200_LOCKSTEP_DP5
-#define ODE_B200_LOCKSTEP_DP5 0 /* 1: Dopri5 with n >= 6 runs lockstep CTAs too (measurement switch) */
+#define ODE_B200_LOCKSTEP_DP5 1 /* 0: Dopri5 with n = 6..8 free-running (measurement switch) */
 #endif
+__host__ __device__ constexpr bool lockstep_small_(int dim, int method) {
+    return ODE_B200_LOCKSTEP_DP5 && method == ODE_B200_DOPRI5 && dim >= 6 && dim <= 8;
+}
 __host__ __device__ constexpr bool lockstep_for(int dim, int method) {
-#ifdef ODE_B200_LOCKSTEP
+#ifdef ODE_B200_LOCKSTEP_ALL /* measurement switch: every adaptive stepper */
+    return method != ODE_B200_RK4;
+#elif defined(ODE_B200_LOCKSTEP)
     return ODE_B200_LOCKSTEP != 0 && (dim > 8 || (dim >= 6 && method == ODE_B200_DOP853));
 #else
-    return dim > 8 || (dim >= 6 && (method == ODE_B200_DOP853 || (ODE_B200_LOCKSTEP_DP5 && method == ODE_B200_DOPRI5)));
+    return dim > 8 || (dim >= 6 && method == ODE_B200_DOP853) || lockstep_small_(dim, method);
 #endif
 }
 /* `records_dense`: the stepper keeps dense-output coefficients live (Dense, Continuous, Continuous8).
@@ -37,7 +47,10 @@ __host__ __device__ constexpr bool lockstep_for(int dim, int method) {
 #define ODE_B200_FREE_THREADS 128 /* CTA size of the steppers that do not run in lockstep (-D: tuning experiments) */
 #endif
 __host__ __device__ constexpr int block_threads_for(int dim, int method, bool records_dense) {
-    return !lockstep_for(dim, method) ? ODE_B200_FREE_THREADS : (dim <= 8 && !records_dense) ? ODE_B200_LOCK_THREADS : 256;
+    return !lockstep_for(dim, method)    ? ODE_B200_FREE_THREADS
+           : lockstep_small_(dim, method) ? 128
+           : (dim <= 8 && !records_dense) ? ODE_B200_LOCK_THREADS
+                                          : 256;
 }
 __host__ __device__ constexpr bool records_dense(int method, int out_type) {
     return method == ODE_B200_DOPRI5 ? (out_type == ODE_B200_OUT_DENSE || out_type == ODE_B200_OUT_CONTINUOUS)

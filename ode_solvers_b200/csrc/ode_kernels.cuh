@@ -84,7 +84,8 @@ constexpr int min_blocks_for() {
 #ifdef ODE_B200_MIN_BLOCKS
     return ODE_B200_MIN_BLOCKS;
 #else
-    if (lockstep_for(N, METHOD)) return 1; /* one CTA per SM */
+    if (lockstep_small_(N, METHOD)) return 4; /* small lockstep CTAs, occupancy as before */
+    if (lockstep_for(N, METHOD)) return 1;    /* one CTA per SM */
     if (N <= 4) return (DENSE || METHOD == ODE_B200_DOP853) ? 4 : 5; /* rcont[][] / 12 stages live: 96 registers spill */
     return 4;
 #endif

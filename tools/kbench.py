@@ -48,6 +48,16 @@ def build(name, n):
         y0, p = W.kepler_sweep(n)
         return ("kepler", ob.config_new(ob.DOPRI5, 0.0, 5.0 * W.kepler_period(), 60.0, 1e-10, 1e-10,
                                         out_type=ob.OUT_SPARSE), y0, p, 0, 487)
+    if name == "kepler_dp5_dense":      # 2335 samples per trajectory (dx = 60 s over 5 periods)
+        y0, p = W.kepler_sweep(n)
+        return ("kepler", ob.config_new(ob.DOPRI5, 0.0, 5.0 * W.kepler_period(), 60.0, 1e-10, 1e-10), y0, p, 2400, 487)
+    if name == "kepler_dp5_com":
+        y0, p = W.kepler_sweep(n)
+        return ("kepler", ob.config_new(ob.DOPRI5, 0.0, 5.0 * W.kepler_period(), 60.0, 1e-10, 1e-10,
+                                        out_type=ob.OUT_CONTINUOUS), y0, p, -1400, 487)
+    if name == "cr3bp_dp5":
+        y0, p = W.cr3bp_ensemble(n)
+        return ("cr3bp", ob.config_new(ob.DOPRI5, 0.0, 20.0, 0.5, 1e-10, 1e-10, out_type=ob.OUT_SPARSE), y0, p, 0, 700)
     if name == "cr3bp_dp8_dense":
         y0, p = W.cr3bp_ensemble(n)
         return "cr3bp", ob.config_new(ob.DOP853, 0.0, 20.0, 0.5, 1e-12, 1e-12), y0, p, 43, 1395
