@@ -23,8 +23,11 @@ namespace ode_b200 {
 #ifndef ODE_B200_LOCKSTEP_DP5
 #define ODE_B200_LOCKSTEP_DP5 1 /* 0: Dopri5 with n = 6..8 free-running (measurement switch) */
 #endif
+#ifndef ODE_B200_LOCKSTEP_SMALL_MIN_DIM
+#define ODE_B200_LOCKSTEP_SMALL_MIN_DIM 6
+#endif
 __host__ __device__ constexpr bool lockstep_small_(int dim, int method) {
-    return ODE_B200_LOCKSTEP_DP5 && method == ODE_B200_DOPRI5 && dim >= 6 && dim <= 8;
+    return ODE_B200_LOCKSTEP_DP5 && method == ODE_B200_DOPRI5 && dim >= ODE_B200_LOCKSTEP_SMALL_MIN_DIM && dim <= 8;
 }
 __host__ __device__ constexpr bool lockstep_for(int dim, int method) {
 #ifdef ODE_B200_LOCKSTEP_ALL /* measurement switch: every adaptive stepper */
