@@ -448,6 +448,7 @@ struct Dop853SplitStepper : SplitCommon<SS, STAGE, 8> {
 #define ODE_B200_SPLIT_THREADS_DENSE 256
 #endif
     static constexpr int kThreads = (DENSE || CONT8) ? ODE_B200_SPLIT_THREADS_DENSE : ODE_B200_SPLIT_THREADS_SPARSE;
+    static constexpr int kMinBlocks = 1; /* 3 x 128 threads: 6.75 (Sparse) / 17.1 ms (Continuous8: 168 registers spill) */
     static constexpr int kRefillIdle = ODE_B200_REFILL_IDLE;
 
     ODE_DEV static void finish(State& s, const KernelArgs& a, const Lane3& L, int status) {
@@ -911,13 +912,16 @@ struct Dopri5SplitStepper : SplitCommon<SS, STAGE, 5> {
     using C::push_step;
     static constexpr bool DENSE = OUT == ODE_B200_OUT_DENSE;
     static constexpr bool CONT = OUT == ODE_B200_OUT_CONTINUOUS;
-#ifndef ODE_B200_SPLIT5_THREADS_SPARSE
-#define ODE_B200_SPLIT5_THREADS_SPARSE ODE_B200_LOCK_THREADS
+    /* three lockstep CTAs of 128 threads per SM (168 registers) instead of one of 384: the same 12 warps, barriers
+     * among 4 of them (3-body, 2^18: Sparse 10.96 -> 10.68 ms, Continuous 16.43 -> 15.22; 2 x 192: 10.90 / 15.77) */
+#ifndef ODE_B200_SPLIT5_THREADS
+#define ODE_B200_SPLIT5_THREADS 128
 #endif
-#ifndef ODE_B200_SPLIT5_THREADS_DENSE
-#define ODE_B200_SPLIT5_THREADS_DENSE ODE_B200_LOCK_THREADS
+#ifndef ODE_B200_SPLIT5_MIN_BLOCKS
+#define ODE_B200_SPLIT5_MIN_BLOCKS 3
 #endif
-    static constexpr int kThreads = (DENSE || CONT) ? ODE_B200_SPLIT5_THREADS_DENSE : ODE_B200_SPLIT5_THREADS_SPARSE;
+    static constexpr int kThreads = ODE_B200_SPLIT5_THREADS;
+    static constexpr int kMinBlocks = ODE_B200_SPLIT5_MIN_BLOCKS;
     static constexpr int kRefillIdle = ODE_B200_REFILL_IDLE;
 
     ODE_DEV static void finish(State& s, const KernelArgs& a, const Lane3& L, int status) {
@@ -1250,7 +1254,7 @@ ODE_DEV void run_lanes_split_(const KernelArgs& a) {
 }
 
 template <class Stepper, bool PIPE = false>
-__global__ void __launch_bounds__(Stepper::kThreads, 1) ode_split_step_loop_kernel(const __grid_constant__ KernelArgs a) {
+__global__ void __launch_bounds__(Stepper::kThreads, Stepper::kMinBlocks) ode_split_step_loop_kernel(const __grid_constant__ KernelArgs a) {
     run_lanes_split_<Stepper, PIPE>(a);
 }
 
