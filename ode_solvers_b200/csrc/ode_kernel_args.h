@@ -46,6 +46,9 @@ __host__ __device__ constexpr bool lockstep_for(int dim, int method) {
 #ifndef ODE_B200_LOCK_THREADS
 #define ODE_B200_LOCK_THREADS 384
 #endif
+#ifndef ODE_B200_LOCK_THREADS_DENSE
+#define ODE_B200_LOCK_THREADS_DENSE 256
+#endif
 #ifndef ODE_B200_FREE_THREADS
 #define ODE_B200_FREE_THREADS 128 /* CTA size of the steppers that do not run in lockstep (-D: tuning experiments) */
 #endif
@@ -53,7 +56,7 @@ __host__ __device__ constexpr int block_threads_for(int dim, int method, bool re
     return !lockstep_for(dim, method)    ? ODE_B200_FREE_THREADS
            : lockstep_small_(dim, method) ? 128
            : (dim <= 8 && !records_dense) ? ODE_B200_LOCK_THREADS
-                                          : 256;
+                                          : ODE_B200_LOCK_THREADS_DENSE;
 }
 __host__ __device__ constexpr bool records_dense(int method, int out_type) {
     return method == ODE_B200_DOPRI5 ? (out_type == ODE_B200_OUT_DENSE || out_type == ODE_B200_OUT_CONTINUOUS)
