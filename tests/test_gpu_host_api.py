@@ -142,6 +142,13 @@ def test_user_system_from_source_matches_builtin_bitwise():
         a = ob.integrate_batch(f, cfg, y0, p, out_cap=cap)
         b = ob.integrate_batch(ob.System.builtin("lorenz"), cfg, y0, p, out_cap=cap)
         assert_same_outputs(a, b, "jit vs builtin m%d" % cfg.method)
+    # Rk4 with every step recorded: the NVRTC build of the warp-level tensor stores (full warps) next to the per-lane
+    # copies (the last, partial warp), capacity no multiple of the group
+    cfg = ob.config_rk4(0.0, 0.013, 1e-3)
+    a = ob.integrate_batch(f, cfg, y0, p, out_cap=14)
+    b = ob.integrate_batch(ob.System.builtin("lorenz"), cfg, y0, p, out_cap=14)
+    assert_same_outputs(a, b, "jit vs builtin, Rk4 recorded")
+    assert (a.out_count == 14).all() and (a.status == ob.OK).all()
 
 
 def test_user_system_div_d_sqrt_d_match_plain_operators_and_builtin():
